@@ -1,0 +1,164 @@
+/*
+ * sgp_b200 — C ABI of the B200 (sm_100a) kernels behind the SGP training-free encoder.
+ *
+ * The reference (Graph-Machine-Learning-Group/sgp) is pure Python and has no FFI of its own:
+ * its "plugin" surface is the Python classes/functions of lib/nn/encoders/*, lib/sgp_preprocessing.py
+ * and lib/nn/reservoir/reservoir.py.  Every entry point below replaces the arithmetic of one of
+ * those call sites (cited per function, paths relative to the reference root) and is what a
+ * maintainer would bind with ctypes from those files (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, strides (in ELEMENTS), a cudaStream_t passed as void*;
+ *     no torch types.
+ *   - every function returns 0 on success, a negative SGP_E* code otherwise; it never throws,
+ *     never allocates (the caller owns every buffer, workspaces are sized by *_workspace_bytes),
+ *     is stream-ordered on `stream`, and is re-entrant across streams.
+ *   - sgp_last_error() returns a thread-local human-readable message for the last failure.
+ *   - all floating point is IEEE fp32 (the reference's precision=32), indices are int32 in the
+ *     CSR (the reference's int64 edge_index is narrowed while building it; N < 2^31, nnz < 2^31).
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef SGP_B200_H
+#define SGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGP_OK 0
+#define SGP_EINVAL (-1)    /* bad shape / flag / null pointer */
+#define SGP_EALIGN (-2)    /* pointer or stride not aligned as the kernel requires */
+#define SGP_ECUDA (-3)     /* CUDA runtime error (message in sgp_last_error) */
+#define SGP_ECAPACITY (-4) /* caller-provided buffer too small */
+#define SGP_EUNSUPPORTED (-5)
+
+/* activation codes (reference: lib/nn/reservoir/reservoir.py:37-41) */
+#define SGP_ACT_TANH 0
+#define SGP_ACT_RELU 1
+#define SGP_ACT_SELF_NORM 2
+#define SGP_ACT_IDENTITY 3
+
+/* sgp_csr_build flags (reference: lib/sgp_preprocessing.py:67-105, 182-185) */
+#define SGP_CSR_SET_DIAG 1     /* set_diag(): drop stored diagonal, insert (i,i)=1 for all i */
+#define SGP_CSR_REMOVE_DIAG 2  /* remove_diag(): drop stored diagonal (ignored when SET_DIAG) */
+#define SGP_CSR_GCN_NORM 4     /* D^-1/2 S D^-1/2 instead of D^-1 S */
+#define SGP_CSR_SYMMETRIZE 8   /* to_undirected(): add reversed edges, coalesce duplicates by add */
+#define SGP_CSR_TRANSPOSE 16   /* swap the two rows of edge_index first (the bidirectional pass) */
+
+int sgp_version(void);
+const char* sgp_last_error(void);
+/* Number of kernels this library has launched in the calling process (for bench accounting). */
+int64_t sgp_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  adjacency -> normalised CSR.
+ * Replaces preprocess_adj (lib/sgp_preprocessing.py:67-105) and the to_undirected /
+ * edge_index[[1,0]] handling of sgp_spatial_embedding (:182-185, :205-207).
+ *   edge_src = edge_index[0] (the COLUMN / source j), edge_dst = edge_index[1] (the ROW / target i)
+ *   (":80  col, row = edge_index").  Entries are ordered by (row, col), duplicates are kept
+ *   (and therefore summed by the SpMM) unless SYMMETRIZE coalesces them.
+ *   weight may be NULL (unit weights).  cap >= 2*E + N is always enough.
+ *   *nnz_out (HOST pointer) receives the number of stored entries; the call synchronises `stream`.
+ * ------------------------------------------------------------------------------------------- */
+size_t sgp_csr_build_workspace_bytes(int64_t E, int32_t N, int flags);
+int sgp_csr_build(const int64_t* edge_src, const int64_t* edge_dst, const float* weight,
+                  int64_t E, int32_t N, int flags,
+                  int32_t* rowptr /*[N+1]*/, int32_t* col /*[cap]*/, float* val /*[cap]*/,
+                  int64_t cap, int64_t* nnz_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  fused leaky-ESN scan of one reservoir layer over a chunk of Tc time steps.
+ * Replaces the Python time loop Reservoir.forward (lib/nn/reservoir/reservoir.py:158-186) around
+ * ReservoirLayer.forward (:77-81):
+ *     h' = (1-alpha) h + alpha * act( x_t W_ih^T + b + h W_hh^T )
+ * for every node n and step t of the chunk; h' is written to out[t, n, 0:H] and carried.
+ *   wpack   [(FinP + H), H] with FinP = Fin rounded up to a multiple of 4: rows 0..Fin-1 = W_ih^T,
+ *           rows Fin..FinP-1 = 0, rows FinP.. = W_hh^T  (made by sgp_reservoir_pack)
+ *   h_state [N, H] in/out: state before the first / after the last step of the chunk
+ *   x       element (t, n, f) at x[t*x_t_stride + n*x_n_stride + f]
+ *   out     element (t, n, j) at out[t*out_t_stride + n*out_n_stride + j]  (a feature block of
+ *           the concatenated [Tc, N, D] encoder output; deeper layers read the previous layer's
+ *           block as their x with Fin = H)
+ * H in {128, 256} with 16-byte aligned out / h_state / wpack and strides % 4 == 0 runs the tiled
+ * FFMA2 kernel; every other shape runs the generic (still CUDA) kernel.
+ * ------------------------------------------------------------------------------------------- */
+int sgp_reservoir_pack(const float* w_ih /*[H,Fin]*/, const float* w_hh /*[H,H]*/, int Fin, int H,
+                       float* wpack /*[(FinP+H),H]*/, void* stream);
+int sgp_reservoir_scan(const float* x, int64_t x_t_stride, int64_t x_n_stride, int Fin,
+                       const float* wpack, const float* bias /*[H]*/,
+                       float alpha, float one_minus_alpha, int act,
+                       float* h_state,
+                       float* out, int64_t out_t_stride, int64_t out_n_stride,
+                       int Tc, int N, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  CSR x dense propagation, batched over the leading (time / batch) axis.
+ * Replaces `x = adj @ x` (lib/sgp_preprocessing.py:200-203; torch_sparse spmm_sum):
+ *     dst[t, i, :] = sum_{e in row i} val[e] * src[t, col[e], :]      i in [0, n_rows)
+ *   row_order  optional [n_rows] permutation: the order in which rows are SCHEDULED (locality),
+ *              results are still written at row i.  NULL = natural order.
+ *   src/dst    element (t, n, f) at p[t*t_stride + n*n_stride + f]; src and dst must not overlap.
+ * sgp_khop_spmm runs `hops` successive hops inside one [Tc, N, D] buffer: hop h reads feature
+ * block (h == 0 ? block_in : block_out0 + h - 1) and writes block block_out0 + h, i.e. it fills
+ * the reference's `res` list (:200-203) directly in its concatenated layout
+ * (lib/nn/encoders/sgp_spatial_encoder.py:35), without the torch.cat copy.
+ * ------------------------------------------------------------------------------------------- */
+int sgp_spmm(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* row_order,
+             const float* src, int64_t src_t_stride, int64_t src_n_stride,
+             float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+             int n_rows, int F, int Tc, void* stream);
+int sgp_khop_spmm(const int32_t* rowptr, const int32_t* col, const float* val,
+                  const int32_t* row_order,
+                  float* buf, int64_t t_stride, int64_t n_stride,
+                  int block_in, int block_out0, int hops, int N, int F, int Tc, void* stream);
+
+/* Row-block-union (RBU) operator: rows are grouped R at a time (R in {4,8,16}); each group stores
+ * the sorted union of its column indices once plus a dense [U, R] value slab, so that every
+ * gathered source row is loaded once per group and reused from registers for R output rows.
+ *   grp_ptr  [n_groups+1] offsets into ucol / uval
+ *   grp_rows [n_groups, R] destination row of each slot (-1 = padding)
+ *   ucol     [total_U]     source row ids
+ *   uval     [total_U, R]  operator values (0 where the row does not have that column)
+ * Requires F % 128 == 0.  Same result as sgp_spmm on the CSR the groups were built from. */
+int sgp_spmm_rbu(const int32_t* grp_ptr, const int32_t* grp_rows, const int32_t* ucol,
+                 const float* uval, int R, int n_groups,
+                 const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                 float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+                 int F, int Tc, void* stream);
+
+/* HOST function (pointers are host memory, no stream): choose the R-row groups of the RBU format
+ * from a CSR operator by a breadth-first, heaviest-neighbour-first greedy (group_rows.cu).
+ * grp_rows must hold ceil(N/R)*R entries; unused slots of the last group are set to -1. */
+int sgp_group_rows(const int32_t* rowptr, const int32_t* col, const float* val, int32_t N, int32_t R,
+                   int32_t* grp_rows, int32_t* n_groups_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  global block: dst[t, n, :] = mean over nodes of src[t, :, :]
+ * Replaces `torch.ones_like(x) * x.mean(-2, keepdim=True)`
+ * (lib/nn/encoders/sgp_spatial_encoder.py:32-34).  `sums` is a [Tc, F] fp32 workspace; when
+ * `precomputed_sums` != 0 it already holds the node SUMS over all shards (after an all-reduce) and
+ * only the broadcast runs; N_total is the divisor.
+ * ------------------------------------------------------------------------------------------- */
+int sgp_node_sum(const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                 float* sums /*[Tc,F]*/, int N, int F, int Tc, void* stream);
+int sgp_node_mean_broadcast(const float* sums /*[Tc,F]*/, int64_t N_total,
+                            float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+                            int N, int F, int Tc, void* stream);
+
+/* Output sink for streamed benchmarking: acc[0] += sum(buf[0:count]) in fp64 (device scalar). */
+int sgp_checksum(const float* buf, int64_t count, double* acc, void* stream);
+
+/* Gather rows: dst[t, i, :] = src[t, index[i], :]  (halo packing for the row-sharded path). */
+int sgp_gather_rows(const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                    const int32_t* index, int n_index,
+                    float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+                    int F, int Tc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGP_B200_H */

@@ -241,7 +241,7 @@ def build_c(force: bool = False) -> str:
     src = os.path.join(_HERE, "sgp_oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         os.makedirs(out_dir, exist_ok=True)
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared",
+        subprocess.check_call(["gcc", "-O3", "-mavx2", "-mfma", "-fopenmp", "-fPIC", "-shared",
                                "-o", so, src, "-lm"])
     return so
 

@@ -1,0 +1,276 @@
+// K2 — CSR x dense propagation over the node graph, batched over time.
+//
+// Replaces `x = adj @ x` of lib/sgp_preprocessing.py:200-203 (torch_sparse spmm_sum) and the
+// torch.cat of lib/nn/encoders/sgp_spatial_encoder.py:35: every hop reads one feature block of
+// the concatenated [Tc, N, D] buffer and writes the next block in place of the `res` list.
+//
+// Two operator formats:
+//   * plain CSR (any graph, any F): one warp per (t, row); the row's (col, val) slice is staged
+//     through a warp-private shared-memory window of 32 edges, every lane then gathers its
+//     float4 slice of the source row (coalesced 512 B per warp-load) and accumulates with packed
+//     FFMA2.  Each gathered row is used for ONE output row -> L1/L2-bandwidth bound.
+//   * RBU (row-block-union, F % 128 == 0): R locality-grouped rows share the union of their
+//     columns; each source row slice is loaded once per group and reused from registers for all
+//     R output rows (dense [U, R] value slab, zeros where a row lacks the column).  Cuts the
+//     L2->SM gather traffic by ~R*deg/U and is the path used on kNN sensor graphs.
+// Bound: HBM nominally (bytes/hop = 8 nnz + 4(N+1) + 8 N F Tc), but at deg 100 / F 256 the fp32
+// FMA pipe (2 nnz F flops) and the L2->SM gather traffic are the tighter limits; see DESIGN.md.
+#include "common.cuh"
+
+namespace sgp {
+
+constexpr int kSpmmWarps = 8;
+
+// ---------------------------------------------------------------------------------------------
+// CSR, vectorised: lane owns NV float4 (columns f0 + q*128 + 4*lane .. +3)
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kSpmmWarps * 32)
+spmm_csr_vec(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+             const float* __restrict__ val, const int32_t* __restrict__ row_order,
+             const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
+             float* __restrict__ dst, int64_t d_ts, int64_t d_ns,
+             int n_rows, int F, long long total /* Tc * n_rows */) {
+    __shared__ int2 stage[kSpmmWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kSpmmWarps + warp;
+    if (gw >= total) return;
+    const int t = (int)(gw / n_rows), r = (int)(gw % n_rows);
+    const int i = row_order ? row_order[r] : r;
+    const int f0 = blockIdx.y * (NV * 128) + lane * 4;
+    const float* sp = src + (size_t)t * s_ts + f0;
+    bool on[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) on[q] = (f0 + q * 128) < F;
+
+    float2 acc[NV][2];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) acc[q][0] = acc[q][1] = make_float2(0.f, 0.f);
+
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    int2* win = stage[warp];
+    for (int base = beg; base < end; base += 32) {
+        const int e = base + lane;
+        int2 cv = make_int2(0, 0);
+        if (e < end) cv = make_int2(__ldg(col + e), __float_as_int(__ldg(val + e)));
+        __syncwarp();
+        win[lane] = cv;
+        __syncwarp();
+        const int cnt = min(32, end - base);
+        int j = 0;
+        for (; j + 4 <= cnt; j += 4) {
+            int2 c[4];
+            float4 xv[4][NV];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = win[j + u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < NV; ++q)
+                    if (on[q]) xv[u][q] = ldg_f4(sp + (size_t)c[u].x * s_ns + q * 128);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < NV; ++q)
+                    if (on[q]) fma4(acc[q][0], acc[q][1], __int_as_float(c[u].y), xv[u][q]);
+        }
+        for (; j < cnt; ++j) {
+            const int2 c = win[j];
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+                if (on[q]) {
+                    const float4 xv = ldg_f4(sp + (size_t)c.x * s_ns + q * 128);
+                    fma4(acc[q][0], acc[q][1], __int_as_float(c.y), xv);
+                }
+        }
+    }
+    float* dp = dst + (size_t)t * d_ts + (size_t)i * d_ns + f0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+        if (on[q]) st_f4(dp + q * 128, make_float4(acc[q][0].x, acc[q][0].y, acc[q][1].x, acc[q][1].y));
+}
+
+// CSR, scalar fallback (F not a multiple of 4 or unaligned views): lane owns columns lane+32q
+__global__ void __launch_bounds__(kSpmmWarps * 32)
+spmm_csr_scalar(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                const float* __restrict__ val, const int32_t* __restrict__ row_order,
+                const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
+                float* __restrict__ dst, int64_t d_ts, int64_t d_ns,
+                int n_rows, int F, long long total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kSpmmWarps + warp;
+    if (gw >= total) return;
+    const int t = (int)(gw / n_rows), r = (int)(gw % n_rows);
+    const int i = row_order ? row_order[r] : r;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    for (int f = blockIdx.y * 128 + lane; f < min(F, (int)(blockIdx.y + 1) * 128); f += 32) {
+        float acc = 0.f;
+        for (int e = beg; e < end; ++e)
+            acc = fmaf(__ldg(val + e), __ldg(src + (size_t)t * s_ts + (size_t)__ldg(col + e) * s_ns + f), acc);
+        dst[(size_t)t * d_ts + (size_t)i * d_ns + f] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RBU: one warp per (t, group, 128-wide feature chunk); lane owns one float4 of R output rows.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kSpmmWarps * 32)
+spmm_rbu_kernel(const int32_t* __restrict__ grp_ptr, const int32_t* __restrict__ grp_rows,
+                const int32_t* __restrict__ ucol, const float* __restrict__ uval,
+                int n_groups, int nfc,
+                const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
+                float* __restrict__ dst, int64_t d_ts, int64_t d_ns, long long total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kSpmmWarps + warp;
+    if (gw >= total) return;
+    const int fc = (int)(gw % nfc);
+    const long long rest = gw / nfc;
+    const int g = (int)(rest % n_groups), t = (int)(rest / n_groups);
+    const float* sp = src + (size_t)t * s_ts + fc * 128 + lane * 4;
+
+    float2 acc[R][2];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+
+    const int beg = grp_ptr[g], end = grp_ptr[g + 1];
+    int u = beg;
+    for (; u + 2 <= end; u += 2) {
+        const int c0 = __ldg(ucol + u), c1 = __ldg(ucol + u + 1);
+        const float4 x0 = ldg_f4(sp + (size_t)c0 * s_ns);
+        const float4 x1 = ldg_f4(sp + (size_t)c1 * s_ns);
+        float4 a0[R / 4], a1[R / 4];
+#pragma unroll
+        for (int k = 0; k < R / 4; ++k) {
+            a0[k] = ldg_f4(uval + (size_t)u * R + k * 4);
+            a1[k] = ldg_f4(uval + (size_t)(u + 1) * R + k * 4);
+        }
+#pragma unroll
+        for (int k = 0; k < R / 4; ++k) {
+            fma4(acc[4 * k + 0][0], acc[4 * k + 0][1], a0[k].x, x0);
+            fma4(acc[4 * k + 1][0], acc[4 * k + 1][1], a0[k].y, x0);
+            fma4(acc[4 * k + 2][0], acc[4 * k + 2][1], a0[k].z, x0);
+            fma4(acc[4 * k + 3][0], acc[4 * k + 3][1], a0[k].w, x0);
+        }
+#pragma unroll
+        for (int k = 0; k < R / 4; ++k) {
+            fma4(acc[4 * k + 0][0], acc[4 * k + 0][1], a1[k].x, x1);
+            fma4(acc[4 * k + 1][0], acc[4 * k + 1][1], a1[k].y, x1);
+            fma4(acc[4 * k + 2][0], acc[4 * k + 2][1], a1[k].z, x1);
+            fma4(acc[4 * k + 3][0], acc[4 * k + 3][1], a1[k].w, x1);
+        }
+    }
+    if (u < end) {
+        const int c0 = __ldg(ucol + u);
+        const float4 x0 = ldg_f4(sp + (size_t)c0 * s_ns);
+#pragma unroll
+        for (int k = 0; k < R / 4; ++k) {
+            const float4 a0 = ldg_f4(uval + (size_t)u * R + k * 4);
+            fma4(acc[4 * k + 0][0], acc[4 * k + 0][1], a0.x, x0);
+            fma4(acc[4 * k + 1][0], acc[4 * k + 1][1], a0.y, x0);
+            fma4(acc[4 * k + 2][0], acc[4 * k + 2][1], a0.z, x0);
+            fma4(acc[4 * k + 3][0], acc[4 * k + 3][1], a0.w, x0);
+        }
+    }
+    float* dp = dst + (size_t)t * d_ts + fc * 128 + lane * 4;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = __ldg(grp_rows + (size_t)g * R + r);
+        if (row >= 0)
+            st_f4(dp + (size_t)row * d_ns, make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y));
+    }
+}
+
+static int check_views(const char* who, const void* src, int64_t s_ts, int64_t s_ns, const void* dst,
+                       int64_t d_ts, int64_t d_ns, int F) {
+    SGP_REQUIRE(src && dst, SGP_EINVAL, "%s: null src/dst", who);
+    SGP_REQUIRE(F >= 1, SGP_EINVAL, "%s: F=%d", who, F);
+    (void)s_ts; (void)s_ns; (void)d_ts; (void)d_ns;
+    return SGP_OK;
+}
+
+static bool vec_views(const void* src, int64_t s_ts, int64_t s_ns, const void* dst, int64_t d_ts,
+                      int64_t d_ns, int F) {
+    return F % 4 == 0 && aligned16(src) && aligned16(dst) && s_ts % 4 == 0 && s_ns % 4 == 0 &&
+           d_ts % 4 == 0 && d_ns % 4 == 0;
+}
+
+}  // namespace sgp
+
+using namespace sgp;
+
+extern "C" int sgp_spmm(const int32_t* rowptr, const int32_t* col, const float* val,
+                        const int32_t* row_order, const float* src, int64_t src_t_stride,
+                        int64_t src_n_stride, float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+                        int n_rows, int F, int Tc, void* stream) {
+    SGP_REQUIRE(rowptr, SGP_EINVAL, "sgp_spmm: null rowptr");
+    SGP_REQUIRE(n_rows >= 0 && Tc >= 0, SGP_EINVAL, "sgp_spmm: n_rows=%d Tc=%d", n_rows, Tc);
+    if (int rc = check_views("sgp_spmm", src, src_t_stride, src_n_stride, dst, dst_t_stride, dst_n_stride, F)) return rc;
+    if (n_rows == 0 || Tc == 0) return SGP_OK;
+    cudaStream_t st = as_stream(stream);
+    const long long total = (long long)Tc * n_rows;
+    const long long blocks = (total + kSpmmWarps - 1) / kSpmmWarps;
+    SGP_REQUIRE(blocks < (1ll << 31), SGP_EUNSUPPORTED, "sgp_spmm: Tc*n_rows too large for one launch");
+    if (vec_views(src, src_t_stride, src_n_stride, dst, dst_t_stride, dst_n_stride, F)) {
+        if (F <= 128) {
+            spmm_csr_vec<1><<<dim3((unsigned)blocks, 1), kSpmmWarps * 32, 0, st>>>(rowptr, col, val, row_order, src, src_t_stride, src_n_stride, dst, dst_t_stride, dst_n_stride, n_rows, F, total);
+        } else {
+            const int ny = (F + 255) / 256;
+            spmm_csr_vec<2><<<dim3((unsigned)blocks, ny), kSpmmWarps * 32, 0, st>>>(rowptr, col, val, row_order, src, src_t_stride, src_n_stride, dst, dst_t_stride, dst_n_stride, n_rows, F, total);
+        }
+        SGP_LAUNCH_CHECK("spmm_csr_vec");
+    } else {
+        const int ny = (F + 127) / 128;
+        spmm_csr_scalar<<<dim3((unsigned)blocks, ny), kSpmmWarps * 32, 0, st>>>(rowptr, col, val, row_order, src, src_t_stride, src_n_stride, dst, dst_t_stride, dst_n_stride, n_rows, F, total);
+        SGP_LAUNCH_CHECK("spmm_csr_scalar");
+    }
+    return SGP_OK;
+}
+
+extern "C" int sgp_khop_spmm(const int32_t* rowptr, const int32_t* col, const float* val,
+                             const int32_t* row_order, float* buf, int64_t t_stride, int64_t n_stride,
+                             int block_in, int block_out0, int hops, int N, int F, int Tc,
+                             void* stream) {
+    SGP_REQUIRE(buf, SGP_EINVAL, "sgp_khop_spmm: null buffer");
+    SGP_REQUIRE(hops >= 0 && block_in >= 0 && block_out0 >= 0, SGP_EINVAL,
+                "sgp_khop_spmm: hops=%d block_in=%d block_out0=%d", hops, block_in, block_out0);
+    SGP_REQUIRE(block_in < block_out0 || block_in >= block_out0 + hops, SGP_EINVAL,
+                "sgp_khop_spmm: input block %d lies inside the output range [%d, %d)", block_in,
+                block_out0, block_out0 + hops);
+    for (int h = 0; h < hops; ++h) {
+        const int bi = (h == 0) ? block_in : block_out0 + h - 1;
+        const int bo = block_out0 + h;
+        int rc = sgp_spmm(rowptr, col, val, row_order, buf + (size_t)bi * F, t_stride, n_stride,
+                          buf + (size_t)bo * F, t_stride, n_stride, N, F, Tc, stream);
+        if (rc) return rc;
+    }
+    return SGP_OK;
+}
+
+extern "C" int sgp_spmm_rbu(const int32_t* grp_ptr, const int32_t* grp_rows, const int32_t* ucol,
+                            const float* uval, int R, int n_groups, const float* src,
+                            int64_t src_t_stride, int64_t src_n_stride, float* dst,
+                            int64_t dst_t_stride, int64_t dst_n_stride, int F, int Tc, void* stream) {
+    SGP_REQUIRE(grp_ptr && grp_rows && ucol && uval, SGP_EINVAL, "sgp_spmm_rbu: null operator");
+    if (int rc = check_views("sgp_spmm_rbu", src, src_t_stride, src_n_stride, dst, dst_t_stride, dst_n_stride, F)) return rc;
+    SGP_REQUIRE(R == 4 || R == 8 || R == 16, SGP_EINVAL, "sgp_spmm_rbu: R=%d (4, 8 or 16)", R);
+    SGP_REQUIRE(F % 128 == 0, SGP_EUNSUPPORTED, "sgp_spmm_rbu: F=%d is not a multiple of 128", F);
+    SGP_REQUIRE(vec_views(src, src_t_stride, src_n_stride, dst, dst_t_stride, dst_n_stride, F) && aligned16(uval),
+                SGP_EALIGN, "sgp_spmm_rbu: views must be 16-byte aligned with strides %% 4 == 0");
+    if (n_groups == 0 || Tc == 0) return SGP_OK;
+    cudaStream_t st = as_stream(stream);
+    const int nfc = F / 128;
+    const long long total = (long long)Tc * n_groups * nfc;
+    const long long blocks = (total + kSpmmWarps - 1) / kSpmmWarps;
+    SGP_REQUIRE(blocks < (1ll << 31), SGP_EUNSUPPORTED, "sgp_spmm_rbu: too many warps for one launch");
+#define SGP_RBU(RR)                                                                              \
+    spmm_rbu_kernel<RR><<<(unsigned)blocks, kSpmmWarps * 32, 0, st>>>(                           \
+        grp_ptr, grp_rows, ucol, uval, n_groups, nfc, src, src_t_stride, src_n_stride, dst,      \
+        dst_t_stride, dst_n_stride, total)
+    if (R == 4) SGP_RBU(4);
+    else if (R == 8) SGP_RBU(8);
+    else SGP_RBU(16);
+#undef SGP_RBU
+    SGP_LAUNCH_CHECK("spmm_rbu");
+    return SGP_OK;
+}

@@ -1,0 +1,145 @@
+// K4 (global-mean block), output checksum sink, halo row gather, and the ABI's error plumbing.
+#include "common.cuh"
+
+namespace sgp {
+
+std::atomic<int64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// sums[t, f] = sum_n src[t, n, f]; grid (ceil(F/128), Tc, node-splits), atomics across splits.
+__global__ void node_sum_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
+                                float* __restrict__ sums, int N, int F) {
+    __shared__ float part[8][128];
+    const int fx = threadIdx.x & 127, ny = threadIdx.x >> 7;   // 1024 threads: 128 features x 8 node lanes
+    const int f = blockIdx.x * 128 + fx, t = blockIdx.y;
+    const int per = (N + gridDim.z - 1) / gridDim.z;
+    const int nb = blockIdx.z * per, ne = min(N, nb + per);
+    float a = 0.f;
+    if (f < F)
+        for (int n = nb + ny; n < ne; n += 8) a += __ldg(src + (size_t)t * s_ts + (size_t)n * s_ns + f);
+    part[ny][fx] = a;
+    __syncthreads();
+    if (ny == 0 && f < F) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += part[k][fx];
+        atomicAdd(sums + (size_t)t * F + f, s);
+    }
+}
+
+__global__ void node_mean_bcast_kernel(const float* __restrict__ sums, float n_total,
+                                       float* __restrict__ dst, int64_t d_ts, int64_t d_ns,
+                                       int N, int F, int Tc) {
+    const int64_t total = (int64_t)Tc * N * F;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const int64_t tn = i / F;
+        const int n = (int)(tn % N), t = (int)(tn / N);
+        dst[(size_t)t * d_ts + (size_t)n * d_ns + f] = sums[(size_t)t * F + f] / n_total;
+    }
+}
+
+__global__ void checksum_kernel(const float* __restrict__ buf, int64_t count, double* acc) {
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x)
+        s += (double)buf[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double w[32];
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? w[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(acc, s);
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
+                                   const int32_t* __restrict__ index, int n_index,
+                                   float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int F, int Tc) {
+    const int64_t total = (int64_t)Tc * n_index * F;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        const int64_t tn = i / F;
+        const int k = (int)(tn % n_index), t = (int)(tn / n_index);
+        dst[(size_t)t * d_ts + (size_t)k * d_ns + f] =
+            __ldg(src + (size_t)t * s_ts + (size_t)__ldg(index + k) * s_ns + f);
+    }
+}
+
+static int grid_1d(int64_t total, int threads) {
+    int64_t g = (total + threads - 1) / threads;
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace sgp
+
+using namespace sgp;
+
+extern "C" int sgp_version(void) { return 100; }
+extern "C" const char* sgp_last_error(void) { return g_err; }
+extern "C" int64_t sgp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int sgp_node_sum(const float* src, int64_t src_t_stride, int64_t src_n_stride, float* sums,
+                            int N, int F, int Tc, void* stream) {
+    SGP_REQUIRE(src && sums, SGP_EINVAL, "sgp_node_sum: null pointer");
+    SGP_REQUIRE(N >= 0 && F >= 1 && Tc >= 0, SGP_EINVAL, "sgp_node_sum: N=%d F=%d Tc=%d", N, F, Tc);
+    if (Tc == 0) return SGP_OK;
+    cudaStream_t st = as_stream(stream);
+    SGP_CUDA(cudaMemsetAsync(sums, 0, (size_t)Tc * F * sizeof(float), st));
+    if (N == 0) return SGP_OK;
+    SGP_REQUIRE(Tc <= 65535, SGP_EUNSUPPORTED, "sgp_node_sum: Tc=%d > 65535", Tc);
+    const int fx = (F + 127) / 128;
+    int splits = (4 * kNumSMs) / (fx * Tc);
+    splits = splits < 1 ? 1 : (splits > (N + 255) / 256 ? (N + 255) / 256 : splits);
+    node_sum_kernel<<<dim3(fx, Tc, splits), 1024, 0, st>>>(src, src_t_stride, src_n_stride, sums, N, F);
+    SGP_LAUNCH_CHECK("node_sum");
+    return SGP_OK;
+}
+
+extern "C" int sgp_node_mean_broadcast(const float* sums, int64_t N_total, float* dst,
+                                       int64_t dst_t_stride, int64_t dst_n_stride, int N, int F, int Tc,
+                                       void* stream) {
+    SGP_REQUIRE(sums && dst, SGP_EINVAL, "sgp_node_mean_broadcast: null pointer");
+    SGP_REQUIRE(N_total >= 1 && N >= 0 && F >= 1 && Tc >= 0, SGP_EINVAL,
+                "sgp_node_mean_broadcast: N_total=%lld N=%d F=%d Tc=%d", (long long)N_total, N, F, Tc);
+    const int64_t total = (int64_t)Tc * N * F;
+    if (total == 0) return SGP_OK;
+    node_mean_bcast_kernel<<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>(
+        sums, (float)N_total, dst, dst_t_stride, dst_n_stride, N, F, Tc);
+    SGP_LAUNCH_CHECK("node_mean_broadcast");
+    return SGP_OK;
+}
+
+extern "C" int sgp_checksum(const float* buf, int64_t count, double* acc, void* stream) {
+    SGP_REQUIRE(buf && acc && count >= 0, SGP_EINVAL, "sgp_checksum: bad arguments");
+    if (count == 0) return SGP_OK;
+    checksum_kernel<<<grid_1d(count, 256 * 8), 256, 0, as_stream(stream)>>>(buf, count, acc);
+    SGP_LAUNCH_CHECK("checksum");
+    return SGP_OK;
+}
+
+extern "C" int sgp_gather_rows(const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                               const int32_t* index, int n_index, float* dst, int64_t dst_t_stride,
+                               int64_t dst_n_stride, int F, int Tc, void* stream) {
+    SGP_REQUIRE(src && dst && (index || n_index == 0), SGP_EINVAL, "sgp_gather_rows: null pointer");
+    const int64_t total = (int64_t)Tc * n_index * F;
+    if (total <= 0) return SGP_OK;
+    gather_rows_kernel<<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>(
+        src, src_t_stride, src_n_stride, index, n_index, dst, dst_t_stride, dst_n_stride, F, Tc);
+    SGP_LAUNCH_CHECK("gather_rows");
+    return SGP_OK;
+}

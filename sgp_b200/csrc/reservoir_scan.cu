@@ -1,0 +1,327 @@
+// K1 — fused leaky-ESN scan (one reservoir layer, a chunk of Tc time steps, all nodes).
+//
+// Replaces the Python loop of lib/nn/reservoir/reservoir.py:158-186 (Reservoir.forward) around
+// :77-81 (ReservoirLayer.forward): two F.linear GEMMs + add + tanh + leaky blend + torch.stack per
+// layer-step become ONE persistent kernel per layer and chunk.  Per node-step the state is read
+// from shared memory, updated, written once to HBM (straight into its feature block of the
+// concatenated encoder output) and never re-read by this kernel.
+//
+// Tiled kernel (H in {128, 256}), 256 threads = 8 warps, 1 CTA / SM:
+//   * warp w owns TM nodes; its A rows  [ x_t (FinP) | h (H) ]  live in shared memory and are
+//     private to the warp (only __syncwarp between steps);
+//   * lane owns H/32 output columns as NQ = H/128 float4 groups (col = q*128 + 4*lane + j), so a
+//     W^T row is read as conflict-free LDS.128 and the output row is written as coalesced STG.128;
+//   * W^T ([FinP+H, H], k-major, made by sgp_reservoir_pack) streams from L2 through a 3-stage
+//     cp.async ring of KC-row chunks shared by the CTA (one __syncthreads per chunk);
+//   * the contraction runs on the fp32 pipe as packed FFMA2 (fma.rn.f32x2, scalar A operand
+//     broadcast) — full fp32, no TF32: a 1000-step recurrence must stay within 1e-4 of the
+//     reference (SURVEY.md §7 "hard parts").
+// Bound: fp32 FMA.  flops / node-step = 2H(Fin+H) + ~6H;  HBM bytes / node-step = 4(Fin + H).
+#include "common.cuh"
+
+namespace sgp {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = 8;
+constexpr int kKC = 16;      // W^T rows per pipeline chunk
+constexpr int kStages = 3;
+
+__device__ __forceinline__ float activate(float v, int act) {
+    if (act == SGP_ACT_TANH) return tanhf(v);
+    if (act == SGP_ACT_RELU) return fmaxf(v, 0.f);
+    return v;  // identity; self_norm is handled by the caller (needs the row norm)
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float f4_get(const float4& v, int i) {
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+template <int H, int TM>
+__global__ void __launch_bounds__(kScanThreads, 1)
+reservoir_scan_tiled(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int Fin, int FinP,
+                     const float* __restrict__ wpack, const float* __restrict__ bias,
+                     float alpha, float oma, int act,
+                     float* __restrict__ h_state,
+                     float* __restrict__ out, int64_t o_ts, int64_t o_ns,
+                     int Tc, int N) {
+    constexpr int NQ = H / 128;
+    constexpr int BM = TM * kScanWarps;
+    extern __shared__ __align__(16) float smem[];
+    const int Ktot = FinP + H;
+    const int LDA = Ktot + 4;
+    float* arow = smem;                      // [BM][LDA]
+    float* wbuf = smem + (size_t)BM * LDA;   // [kStages][kKC][H]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.x * BM + warp * TM;   // first node of this warp
+    float* myrow = arow + (size_t)warp * TM * LDA;
+
+    // ---- initial state and zero padding of the x slot --------------------------------
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+        const int n = n0 + m;
+        for (int f = lane; f < FinP; f += 32) myrow[m * LDA + f] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < N) v = *reinterpret_cast<const float4*>(h_state + (size_t)n * H + q * 128 + lane * 4);
+            *reinterpret_cast<float4*>(myrow + m * LDA + FinP + q * 128 + lane * 4) = v;
+        }
+    }
+    float4 bq[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) bq[q] = ldg_f4(bias + q * 128 + lane * 4);
+
+    const int NCH = (Ktot + kKC - 1) / kKC;
+    const long long total = (long long)Tc * NCH;
+    auto issue = [&](long long g) {
+        if (g < total) {
+            const int c = (int)(g % NCH);
+            const int rows = min(kKC, Ktot - c * kKC);
+            const float* src = wpack + (size_t)c * kKC * H;
+            float* dst = wbuf + (size_t)(g % kStages) * kKC * H;
+            for (int i = tid; i < rows * (H / 4); i += kScanThreads) cp_async16(dst + i * 4, src + i * 4);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+
+    long long g = 0;
+    for (int t = 0; t < Tc; ++t) {
+        // ---- stage x_t into the warp-private A rows ----------------------------------
+        const float* xt = x + (size_t)t * x_ts;
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            const int n = n0 + m;
+            for (int f = lane; f < Fin; f += 32)
+                myrow[m * LDA + f] = (n < N) ? __ldg(xt + (size_t)n * x_ns + f) : 0.f;
+        }
+        __syncwarp();
+
+        float2 acc[TM][NQ][2];
+#pragma unroll
+        for (int m = 0; m < TM; ++m)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                acc[m][q][0] = make_float2(bq[q].x, bq[q].y);
+                acc[m][q][1] = make_float2(bq[q].z, bq[q].w);
+            }
+
+        for (int c = 0; c < NCH; ++c, ++g) {
+            cp_async_wait<1>();
+            __syncthreads();
+            issue(g + 2);
+            const float* wst = wbuf + (size_t)(g % kStages) * kKC * H + lane * 4;
+            const int rows = min(kKC, Ktot - c * kKC);
+            const float* ap = myrow + c * kKC;
+            for (int kq = 0; kq < rows; kq += 4) {
+                float4 a[TM];
+#pragma unroll
+                for (int m = 0; m < TM; ++m) a[m] = *reinterpret_cast<const float4*>(ap + m * LDA + kq);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    float4 w[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        w[q] = *reinterpret_cast<const float4*>(wst + (kq + kk) * H + q * 128);
+#pragma unroll
+                    for (int m = 0; m < TM; ++m) {
+                        const float av = f4_get(a[m], kk);
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) fma4(acc[m][q][0], acc[m][q][1], av, w[q]);
+                    }
+                }
+            }
+        }
+        __syncwarp();   // every lane is done reading this warp's A rows
+
+        // ---- epilogue: activation, leaky blend, write state (smem) and output (HBM) ----
+        float* ot = out + (size_t)t * o_ts;
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            const int n = n0 + m;
+            float scale = 1.f;
+            if (act == SGP_ACT_SELF_NORM) {
+                float ss = 0.f;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    ss += acc[m][q][0].x * acc[m][q][0].x + acc[m][q][0].y * acc[m][q][0].y +
+                          acc[m][q][1].x * acc[m][q][1].x + acc[m][q][1].y * acc[m][q][1].y;
+                }
+                ss = warp_sum(ss);
+                scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                float* hp = myrow + m * LDA + FinP + q * 128 + lane * 4;
+                const float4 ho = *reinterpret_cast<const float4*>(hp);
+                float4 z = make_float4(acc[m][q][0].x, acc[m][q][0].y, acc[m][q][1].x, acc[m][q][1].y);
+                if (act == SGP_ACT_SELF_NORM) {
+                    z.x *= scale; z.y *= scale; z.z *= scale; z.w *= scale;
+                } else {
+                    z.x = activate(z.x, act); z.y = activate(z.y, act);
+                    z.z = activate(z.z, act); z.w = activate(z.w, act);
+                }
+                float4 hn;
+                hn.x = oma * ho.x + alpha * z.x;
+                hn.y = oma * ho.y + alpha * z.y;
+                hn.z = oma * ho.z + alpha * z.z;
+                hn.w = oma * ho.w + alpha * z.w;
+                *reinterpret_cast<float4*>(hp) = hn;
+                if (n < N) st_f4(ot + (size_t)n * o_ns + q * 128 + lane * 4, hn);
+            }
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+
+    // ---- carry the state to the next chunk ------------------------------------------------
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+        const int n = n0 + m;
+        if (n < N) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                *reinterpret_cast<float4*>(h_state + (size_t)n * H + q * 128 + lane * 4) =
+                    *reinterpret_cast<const float4*>(myrow + m * LDA + FinP + q * 128 + lane * 4);
+        }
+    }
+}
+
+// Generic kernel: any H, any Fin.  One warp per node, lanes stride over the output columns,
+// W^T read through L1/L2 (coalesced over the column index), A row [x_t | h] in shared memory.
+constexpr int kGenWarps = 8;
+__global__ void __launch_bounds__(kGenWarps * 32)
+reservoir_scan_generic(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int Fin, int FinP,
+                       const float* __restrict__ wpack, const float* __restrict__ bias,
+                       float alpha, float oma, int act,
+                       float* __restrict__ h_state,
+                       float* __restrict__ out, int64_t o_ts, int64_t o_ns,
+                       int Tc, int N, int H) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x * kGenWarps + warp;
+    const int Ktot = FinP + H;
+    float* a = smem + (size_t)warp * (Ktot + H);   // [x | h]
+    float* hn = a + Ktot;                          // new state
+    if (n >= N) return;                            // warps are independent: no CTA barrier below
+    for (int f = lane; f < FinP; f += 32) a[f] = 0.f;
+    for (int j = lane; j < H; j += 32) a[FinP + j] = h_state[(size_t)n * H + j];
+    __syncwarp();
+    for (int t = 0; t < Tc; ++t) {
+        for (int f = lane; f < Fin; f += 32) a[f] = __ldg(x + (size_t)t * x_ts + (size_t)n * x_ns + f);
+        __syncwarp();
+        float ss = 0.f;
+        for (int j = lane; j < H; j += 32) {
+            float s = __ldg(bias + j);
+            for (int k = 0; k < Ktot; ++k) s = fmaf(a[k], __ldg(wpack + (size_t)k * H + j), s);
+            hn[j] = s;
+            ss += s * s;
+        }
+        float scale = 1.f;
+        if (act == SGP_ACT_SELF_NORM) scale = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+        __syncwarp();
+        for (int j = lane; j < H; j += 32) {
+            const float z = (act == SGP_ACT_SELF_NORM) ? hn[j] * scale : activate(hn[j], act);
+            const float v = oma * a[FinP + j] + alpha * z;
+            a[FinP + j] = v;
+            out[(size_t)t * o_ts + (size_t)n * o_ns + j] = v;
+        }
+        __syncwarp();
+    }
+    for (int j = lane; j < H; j += 32) h_state[(size_t)n * H + j] = a[FinP + j];
+}
+
+__global__ void reservoir_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                      int Fin, int FinP, int H, float* __restrict__ wpack) {
+    const int64_t total = (int64_t)(FinP + H) * H;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / H), n = (int)(i % H);
+        float v = 0.f;
+        if (k < Fin) v = w_ih[(size_t)n * Fin + k];
+        else if (k >= FinP) v = w_hh[(size_t)n * H + (k - FinP)];
+        wpack[i] = v;
+    }
+}
+
+template <int H, int TM>
+static int launch_tiled(const float* x, int64_t x_ts, int64_t x_ns, int Fin, int FinP,
+                        const float* wpack, const float* bias, float alpha, float oma, int act,
+                        float* h_state, float* out, int64_t o_ts, int64_t o_ns, int Tc, int N,
+                        cudaStream_t st) {
+    constexpr int BM = TM * kScanWarps;
+    const size_t smem = ((size_t)BM * (FinP + H + 4) + (size_t)kStages * kKC * H) * sizeof(float);
+    if (smem > 227 * 1024) return 1;   // caller falls back to a smaller TM
+    auto kern = reservoir_scan_tiled<H, TM>;
+    SGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (N + BM - 1) / BM;
+    kern<<<grid, kScanThreads, smem, st>>>(x, x_ts, x_ns, Fin, FinP, wpack, bias, alpha, oma, act,
+                                           h_state, out, o_ts, o_ns, Tc, N);
+    SGP_LAUNCH_CHECK("reservoir_scan_tiled");
+    return SGP_OK;
+}
+
+}  // namespace sgp
+
+using namespace sgp;
+
+extern "C" int sgp_reservoir_pack(const float* w_ih, const float* w_hh, int Fin, int H, float* wpack,
+                                  void* stream) {
+    SGP_REQUIRE(w_ih && w_hh && wpack, SGP_EINVAL, "sgp_reservoir_pack: null pointer");
+    SGP_REQUIRE(Fin >= 1 && H >= 1, SGP_EINVAL, "sgp_reservoir_pack: Fin=%d H=%d", Fin, H);
+    const int FinP = (Fin + 3) & ~3;
+    const int64_t total = (int64_t)(FinP + H) * H;
+    const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    reservoir_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_ih, w_hh, Fin, FinP, H, wpack);
+    SGP_LAUNCH_CHECK("reservoir_pack");
+    return SGP_OK;
+}
+
+extern "C" int sgp_reservoir_scan(const float* x, int64_t x_t_stride, int64_t x_n_stride, int Fin,
+                                  const float* wpack, const float* bias, float alpha,
+                                  float one_minus_alpha, int act, float* h_state, float* out,
+                                  int64_t out_t_stride, int64_t out_n_stride, int Tc, int N, int H,
+                                  void* stream) {
+    SGP_REQUIRE(x && wpack && bias && h_state && out, SGP_EINVAL, "sgp_reservoir_scan: null pointer");
+    SGP_REQUIRE(Fin >= 1 && H >= 1 && N >= 0 && Tc >= 0, SGP_EINVAL,
+                "sgp_reservoir_scan: Fin=%d H=%d N=%d Tc=%d", Fin, H, N, Tc);
+    SGP_REQUIRE(act >= SGP_ACT_TANH && act <= SGP_ACT_IDENTITY, SGP_EINVAL,
+                "sgp_reservoir_scan: unknown activation code %d", act);
+    if (N == 0 || Tc == 0) return SGP_OK;
+    cudaStream_t st = as_stream(stream);
+    const int FinP = (Fin + 3) & ~3;
+    const bool vec_ok = aligned16(out) && aligned16(h_state) && aligned16(wpack) && aligned16(bias) &&
+                        out_t_stride % 4 == 0 && out_n_stride % 4 == 0;
+    if ((H == 128 || H == 256) && vec_ok) {
+        int rc = 1;
+        // enough CTAs to fill the machine first, then the widest tile that fits shared memory
+        if (H == 256) {
+            if (N >= 64 * kNumSMs) rc = launch_tiled<256, 8>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
+            if (rc == 1 && N >= 32 * kNumSMs) rc = launch_tiled<256, 4>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
+            if (rc == 1) rc = launch_tiled<256, 2>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
+        } else {
+            if (N >= 64 * kNumSMs) rc = launch_tiled<128, 8>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
+            if (rc == 1 && N >= 32 * kNumSMs) rc = launch_tiled<128, 4>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
+            if (rc == 1) rc = launch_tiled<128, 2>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
+        }
+        if (rc != 1) return rc;
+    }
+    const size_t smem = (size_t)kGenWarps * (FinP + 2 * (size_t)H) * sizeof(float);
+    SGP_REQUIRE(smem <= 227 * 1024, SGP_EUNSUPPORTED,
+                "sgp_reservoir_scan: Fin=%d H=%d needs %zu B of shared memory", Fin, H, smem);
+    SGP_CUDA(cudaFuncSetAttribute(reservoir_scan_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    reservoir_scan_generic<<<(N + kGenWarps - 1) / kGenWarps, kGenWarps * 32, smem, st>>>(
+        x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out,
+        out_t_stride, out_n_stride, Tc, N, H);
+    SGP_LAUNCH_CHECK("reservoir_scan_generic");
+    return SGP_OK;
+}

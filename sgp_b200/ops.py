@@ -1,0 +1,221 @@
+"""Thin torch-tensor wrappers over the C ABI (device pointers, strides, current stream).
+
+All tensors must live on a CUDA device; nothing here computes on the host.  `view3` arguments are
+[T, N, F] float32 views whose last dimension is contiguous (feature blocks of a wider buffer are
+fine: their t / n strides are passed through).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_CODES, check, load
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.SgpError("sgp_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+def _check_view3(t: torch.Tensor, name: str):
+    if t.dim() != 3 or t.dtype != torch.float32 or (t.size(-1) > 1 and t.stride(-1) != 1):
+        raise ValueError(f"{name}: expected a float32 [T, N, F] view with contiguous features, got "
+                         f"{tuple(t.shape)} {t.dtype} strides {t.stride()}")
+
+
+@dataclass
+class Csr:
+    """Normalised shift operator in CSR (device, int32 indices)."""
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    val: torch.Tensor
+    num_nodes: int
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+
+def csr_build(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int,
+              flags: int) -> Csr:
+    """Device CSR from a [2, E] int64 edge list in the reference convention ([0]=col, [1]=row)."""
+    _require_cuda(edge_index, edge_weight)
+    lib = load()
+    dev = edge_index.device
+    ei = edge_index.to(torch.int64).contiguous()
+    E = int(ei.size(1))
+    w = None if edge_weight is None else edge_weight.to(torch.float32).contiguous()
+    if w is not None and w.numel() != E:
+        raise ValueError(f"edge_weight has {w.numel()} entries for {E} edges")
+    N = int(num_nodes)
+    cap = (2 * E if flags & _lib.CSR_SYMMETRIZE else E) + (N if flags & _lib.CSR_SET_DIAG else 0)
+    cap = max(cap, 1)
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(cap, dtype=torch.int32, device=dev)
+    val = torch.empty(cap, dtype=torch.float32, device=dev)
+    ws_bytes = int(lib.sgp_csr_build_workspace_bytes(E, N, flags))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    nnz = ctypes.c_int64(0)
+    src, dst = (ei[0], ei[1]) if E else (None, None)
+    check(lib.sgp_csr_build(_p(src), _p(dst), _p(w), E, N, flags, _p(rowptr), _p(col), _p(val), cap,
+                            ctypes.byref(nnz), _p(ws), ws_bytes, _stream(dev)), "sgp_csr_build")
+    n = int(nnz.value)
+    return Csr(rowptr, col[:n], val[:n], N)
+
+
+def reservoir_pack(w_ih: torch.Tensor, w_hh: torch.Tensor) -> torch.Tensor:
+    _require_cuda(w_ih, w_hh)
+    H, Fin = w_ih.shape
+    FinP = (Fin + 3) // 4 * 4
+    out = torch.empty(FinP + H, H, dtype=torch.float32, device=w_ih.device)
+    check(load().sgp_reservoir_pack(_p(w_ih.contiguous()), _p(w_hh.contiguous()), Fin, H, _p(out),
+                                    _stream(w_ih.device)), "sgp_reservoir_pack")
+    return out
+
+
+def reservoir_scan(x: torch.Tensor, wpack: torch.Tensor, bias: torch.Tensor, alpha: float,
+                   activation: str, h_state: torch.Tensor, out: torch.Tensor) -> None:
+    """One layer over a chunk: x [Tc,N,Fin] view, h_state [N,H] in/out, out [Tc,N,H] view."""
+    _require_cuda(x, wpack, bias, h_state, out)
+    _check_view3(x, "x")
+    _check_view3(out, "out")
+    Tc, N, Fin = x.shape
+    H = int(bias.numel())
+    assert out.shape == (Tc, N, H) and h_state.shape == (N, H) and h_state.is_contiguous()
+    a = float(alpha)
+    check(load().sgp_reservoir_scan(_p(x), x.stride(0), x.stride(1), Fin, _p(wpack), _p(bias),
+                                    a, float(1.0 - a), ACT_CODES[activation], _p(h_state),
+                                    _p(out), out.stride(0), out.stride(1), Tc, N, H,
+                                    _stream(x.device)), "sgp_reservoir_scan")
+
+
+def spmm(csr: Csr, src: torch.Tensor, dst: torch.Tensor, row_order: Optional[torch.Tensor] = None,
+         n_rows: Optional[int] = None) -> None:
+    _require_cuda(src, dst, csr.rowptr)
+    _check_view3(src, "src")
+    _check_view3(dst, "dst")
+    Tc, _, F = src.shape
+    rows = int(csr.rowptr.numel() - 1) if n_rows is None else n_rows
+    assert dst.shape[0] == Tc and dst.shape[2] == F and dst.shape[1] >= rows
+    check(load().sgp_spmm(_p(csr.rowptr), _p(csr.col), _p(csr.val), _p(row_order),
+                          _p(src), src.stride(0), src.stride(1), _p(dst), dst.stride(0), dst.stride(1),
+                          rows, F, Tc, _stream(src.device)), "sgp_spmm")
+
+
+def khop_spmm(csr: Csr, buf: torch.Tensor, block_in: int, block_out0: int, hops: int, F: int,
+              row_order: Optional[torch.Tensor] = None) -> None:
+    _require_cuda(buf)
+    _check_view3(buf, "buf")
+    Tc, N, _ = buf.shape
+    check(load().sgp_khop_spmm(_p(csr.rowptr), _p(csr.col), _p(csr.val), _p(row_order), _p(buf),
+                               buf.stride(0), buf.stride(1), block_in, block_out0, hops, N, F, Tc,
+                               _stream(buf.device)), "sgp_khop_spmm")
+
+
+@dataclass
+class Rbu:
+    """Row-block-union operator (see include/sgp_b200.h)."""
+    grp_ptr: torch.Tensor
+    grp_rows: torch.Tensor
+    ucol: torch.Tensor
+    uval: torch.Tensor
+    R: int
+    n_groups: int
+    fill: float
+
+
+def group_rows_host(rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, N: int, R: int) -> np.ndarray:
+    """Host greedy grouping (csrc/group_rows.cu): returns grp_rows [n_groups, R] int32."""
+    lib = load()
+    n_groups = (N + R - 1) // R
+    out = np.empty(max(n_groups * R, 1), np.int32)
+    got = ctypes.c_int32(0)
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    col = np.ascontiguousarray(col, np.int32)
+    val = np.ascontiguousarray(val, np.float32)
+    check(lib.sgp_group_rows(rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, N, R,
+                             out.ctypes.data, ctypes.byref(got)), "sgp_group_rows")
+    return out[: n_groups * R].reshape(n_groups, R)
+
+
+def rbu_build(csr: Csr, R: int) -> Rbu:
+    """Group rows on the host (needs the CSR there once), then assemble the union slabs on the
+    device with sort/unique/scatter (one-off, O(nnz))."""
+    dev = csr.rowptr.device
+    N = csr.num_nodes
+    grp_rows_h = group_rows_host(csr.rowptr.cpu().numpy(), csr.col.cpu().numpy(),
+                                 csr.val.cpu().numpy(), N, R)
+    n_groups = grp_rows_h.shape[0]
+    grp_rows = torch.from_numpy(grp_rows_h).to(dev)
+    flat = grp_rows.reshape(-1).to(torch.int64)
+    valid = flat >= 0
+    slot_of = torch.empty(N, dtype=torch.int64, device=dev)
+    slot_of[flat[valid]] = torch.arange(flat.numel(), device=dev)[valid]      # g*R + slot
+    counts = (csr.rowptr[1:] - csr.rowptr[:-1]).to(torch.int64)
+    row_of_e = torch.repeat_interleave(torch.arange(N, device=dev), counts)
+    gs = slot_of[row_of_e]
+    g_e, s_e = gs // R, gs % R
+    key = g_e * N + csr.col.to(torch.int64)
+    ukey, inv = torch.unique(key, return_inverse=True)
+    total_u = int(ukey.numel())
+    ucol = (ukey % N).to(torch.int32)
+    ugrp = ukey // N
+    grp_ptr = torch.zeros(n_groups + 1, dtype=torch.int64, device=dev)
+    grp_ptr[1:] = torch.cumsum(torch.bincount(ugrp, minlength=n_groups), 0)
+    uval = torch.zeros(max(total_u, 1), R, dtype=torch.float32, device=dev)
+    uval.index_put_((inv, s_e), csr.val, accumulate=True)
+    fill = csr.nnz / max(total_u * R, 1)
+    return Rbu(grp_ptr.to(torch.int32), grp_rows.contiguous(), ucol, uval, R, n_groups, fill)
+
+
+def spmm_rbu(rbu: Rbu, src: torch.Tensor, dst: torch.Tensor) -> None:
+    _require_cuda(src, dst)
+    _check_view3(src, "src")
+    _check_view3(dst, "dst")
+    Tc, _, F = src.shape
+    check(load().sgp_spmm_rbu(_p(rbu.grp_ptr), _p(rbu.grp_rows), _p(rbu.ucol), _p(rbu.uval), rbu.R,
+                              rbu.n_groups, _p(src), src.stride(0), src.stride(1), _p(dst),
+                              dst.stride(0), dst.stride(1), F, Tc, _stream(src.device)), "sgp_spmm_rbu")
+
+
+def node_sum(src: torch.Tensor, sums: torch.Tensor) -> None:
+    _check_view3(src, "src")
+    Tc, N, F = src.shape
+    assert sums.shape == (Tc, F) and sums.is_contiguous()
+    check(load().sgp_node_sum(_p(src), src.stride(0), src.stride(1), _p(sums), N, F, Tc,
+                              _stream(src.device)), "sgp_node_sum")
+
+
+def node_mean_broadcast(sums: torch.Tensor, n_total: int, dst: torch.Tensor) -> None:
+    _check_view3(dst, "dst")
+    Tc, N, F = dst.shape
+    check(load().sgp_node_mean_broadcast(_p(sums), n_total, _p(dst), dst.stride(0), dst.stride(1),
+                                         N, F, Tc, _stream(dst.device)), "sgp_node_mean_broadcast")
+
+
+def checksum(buf: torch.Tensor, acc: torch.Tensor) -> None:
+    assert buf.is_contiguous() and buf.dtype == torch.float32 and acc.dtype == torch.float64
+    check(load().sgp_checksum(_p(buf), buf.numel(), _p(acc), _stream(buf.device)), "sgp_checksum")
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> None:
+    _check_view3(src, "src")
+    _check_view3(dst, "dst")
+    Tc, _, F = src.shape
+    check(load().sgp_gather_rows(_p(src), src.stride(0), src.stride(1), _p(index), int(index.numel()),
+                                 _p(dst), dst.stride(0), dst.stride(1), F, Tc, _stream(src.device)),
+          "sgp_gather_rows")

@@ -1,0 +1,251 @@
+"""Spatial propagation — host side of kernels K2/K3/K4.
+
+Same function names and arguments as the reference's ``lib/sgp_preprocessing.py``
+(``preprocess_adj``, ``sgp_spatial_embedding``, ``reservoir_preprocessing_``,
+``preprocess_dataset``); the sparse algebra that the reference delegates to torch_sparse /
+torch_geometric runs in the sm_100a kernels behind ``include/sgp_b200.h``:
+
+* ``preprocess_adj`` returns a :class:`ShiftOperator` (device CSR, optionally also the RBU
+  format) where the reference returns a ``torch_sparse.SparseTensor``; it supports ``op @ x``.
+* ``sgp_spatial_embedding`` fills one concatenated ``[B, N, (1+K')F]`` buffer hop by hop (no
+  ``torch.cat``) and returns the reference's list as views of it.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+from ._lib import SgpError
+from .reservoir import Reservoir, _cuda_device_for
+
+# rows are grouped for the RBU kernel when the graph is big enough for gather traffic to matter
+_RBU_MIN_NNZ = int(os.environ.get("SGP_B200_RBU_MIN_NNZ", 200_000))
+_RBU_MIN_FILL = {16: 0.30, 8: 0.40, 4: 0.55}
+
+
+class ShiftOperator:
+    """Normalised graph-shift operator resident on one GPU (what ``preprocess_adj`` returns)."""
+
+    def __init__(self, csr: ops.Csr, rbu: Optional[ops.Rbu] = None):
+        self.csr = csr
+        self.rbu = rbu
+        self.num_nodes = csr.num_nodes
+
+    @property
+    def device(self):
+        return self.csr.rowptr.device
+
+    def sparse_sizes(self):
+        return (self.num_nodes, self.num_nodes)
+
+    def nnz(self) -> int:
+        return self.csr.nnz
+
+    def csr_arrays(self):
+        """(rowptr, col, val) as they would come out of SparseTensor.csr() (int32 indices)."""
+        return self.csr.rowptr, self.csr.col, self.csr.val
+
+    def maybe_build_rbu(self, F: int, mode: str = "auto") -> None:
+        """Attach the RBU format when it pays: F % 128 == 0 and the greedy groups are dense enough."""
+        if self.rbu is not None or mode == "off" or F % 128 != 0:
+            return
+        if mode == "auto" and self.csr.nnz < _RBU_MIN_NNZ:
+            return
+        if mode.startswith("force"):
+            self.rbu = ops.rbu_build(self.csr, int(mode[len("force"):]))
+            return
+        for R in (16, 8, 4):
+            cand = ops.rbu_build(self.csr, R)
+            if cand.fill >= _RBU_MIN_FILL[R]:
+                self.rbu = cand
+                return
+
+    def apply(self, src: Tensor, dst: Tensor) -> None:
+        """dst[t] = S @ src[t] for [T, N, F] device views (dst must not alias src)."""
+        F = src.size(-1)
+        if (self.rbu is not None and F % 128 == 0 and src.data_ptr() % 16 == 0 and
+                dst.data_ptr() % 16 == 0 and all(s % 4 == 0 for s in (*src.stride()[:2], *dst.stride()[:2]))):
+            ops.spmm_rbu(self.rbu, src, dst)
+        else:
+            ops.spmm(self.csr, src, dst)
+
+    def __matmul__(self, x: Tensor) -> Tensor:
+        """``adj @ x`` for x [N, F] or [..., N, F]; result on x's device."""
+        dev = self.device
+        xd = x.detach().to(device=dev, dtype=torch.float32)
+        lead = xd.shape[:-2]
+        x3 = xd.reshape(-1, xd.size(-2), xd.size(-1)).contiguous()
+        out = torch.empty_like(x3)
+        self.apply(x3, out)
+        return out.reshape(*lead, *out.shape[-2:]).to(x.device)
+
+
+Adj = Union[Tensor, np.ndarray, ShiftOperator]
+
+
+def _edges_to_device(edge_index, edge_weight, device):
+    if isinstance(edge_index, np.ndarray):                       # sgp_preprocessing.py:73-76
+        edge_index = torch.from_numpy(edge_index)
+        if edge_weight is not None and isinstance(edge_weight, np.ndarray):
+            edge_weight = torch.from_numpy(edge_weight)
+    if not isinstance(edge_index, Tensor):
+        raise RuntimeError("Edge index must be (edge_index, edge_weight) tuple "
+                           "or SparseTensor.")
+    ei = edge_index.to(device=device, dtype=torch.int64)
+    ew = None if edge_weight is None else torch.as_tensor(edge_weight).to(device=device,
+                                                                          dtype=torch.float32)
+    return ei, ew
+
+
+def build_operator(edge_index, edge_weight, num_nodes: int, *, gcn_norm=False, set_diag=False,
+                   remove_diag=False, symmetrize=False, transpose=False, device=None) -> ShiftOperator:
+    if device is None:
+        device = _cuda_device_for(edge_index if isinstance(edge_index, Tensor) else torch.empty(0))
+    ei, ew = _edges_to_device(edge_index, edge_weight, device)
+    flags = ((_lib.CSR_SET_DIAG if set_diag else 0) | (_lib.CSR_REMOVE_DIAG if remove_diag else 0) |
+             (_lib.CSR_GCN_NORM if gcn_norm else 0) | (_lib.CSR_SYMMETRIZE if symmetrize else 0) |
+             (_lib.CSR_TRANSPOSE if transpose else 0))
+    return ShiftOperator(ops.csr_build(ei, ew, int(num_nodes), flags))
+
+
+def preprocess_adj(edge_index: Adj, edge_weight: Optional[Tensor] = None,
+                   num_nodes: Optional[int] = None, gcn_norm: bool = False, set_diag: bool = True,
+                   remove_diag: bool = False) -> ShiftOperator:
+    """Reference: lib/sgp_preprocessing.py:67-105.  An already-built :class:`ShiftOperator` is
+    passed through (the counterpart of handing the reference a SparseTensor, which it would
+    re-normalise; ours is normalised at construction)."""
+    if isinstance(edge_index, ShiftOperator):
+        return edge_index
+    if not isinstance(edge_index, (Tensor, np.ndarray)):
+        raise RuntimeError("Edge index must be (edge_index, edge_weight) tuple "
+                           "or SparseTensor.")
+    if num_nodes is None:
+        ei = torch.as_tensor(edge_index)
+        num_nodes = int(ei.max()) + 1 if ei.numel() else 0
+    return build_operator(edge_index, edge_weight, num_nodes, gcn_norm=gcn_norm, set_diag=set_diag,
+                          remove_diag=remove_diag)
+
+
+def _dropout_edges(edge_index, edge_weight, p: float):
+    """torch_geometric.utils.dropout_adj (PyG 2.0) with training=True: identity at p == 0,
+    otherwise keep each edge with probability 1 - p."""
+    if p < 0. or p > 1.:
+        raise ValueError(f'Dropout probability has to be between 0 and 1 (got {p}')
+    if p == 0.0:
+        return edge_index, edge_weight
+    ei = torch.as_tensor(edge_index)
+    keep = torch.bernoulli(torch.full((ei.size(1),), 1 - p, device=ei.device)).to(torch.bool)
+    ew = None if edge_weight is None else torch.as_tensor(edge_weight)[keep]
+    return ei[:, keep], ew
+
+
+def spatial_blocks(k: int, bidirectional: bool) -> int:
+    return 1 + k * (2 if bidirectional else 1)
+
+
+def propagate_into(buf: Tensor, F: int, k: int, fwd: ShiftOperator,
+                   bwd: Optional[ShiftOperator]) -> None:
+    """buf [T, N, >= blocks*F] on the device with block 0 filled: write S^h x into block h for
+    h = 1..k and, with `bwd`, the k hops of the reversed operator into blocks k+1..2k
+    (the order of the reference's ``res`` list, sgp_preprocessing.py:200-217)."""
+    for h in range(1, k + 1):
+        fwd.apply(buf[..., (h - 1) * F:h * F], buf[..., h * F:(h + 1) * F])
+    if bwd is not None:
+        for h in range(1, k + 1):
+            src = buf[..., :F] if h == 1 else buf[..., (k + h - 1) * F:(k + h) * F]
+            bwd.apply(src, buf[..., (k + h) * F:(k + h + 1) * F])
+
+
+def make_operators(edge_index, edge_weight, num_nodes, *, undirected, add_self_loops,
+                   remove_self_loops, bidirectional, device, F: int = 0, rbu: str = "auto"):
+    """Forward (and reversed) operators exactly as sgp_spatial_embedding builds them (:182-192,
+    :205-216)."""
+    if undirected:
+        assert bidirectional is False
+    if isinstance(edge_index, ShiftOperator):
+        fwd, bwd = edge_index, None
+        if bidirectional:
+            raise SgpError("bidirectional propagation needs the edge list, not a built operator")
+    else:
+        fwd = build_operator(edge_index, edge_weight, num_nodes, gcn_norm=undirected,
+                             set_diag=add_self_loops, remove_diag=remove_self_loops,
+                             symmetrize=undirected, device=device)
+        bwd = None
+        if bidirectional:
+            bwd = build_operator(edge_index, edge_weight, num_nodes, gcn_norm=False,
+                                 set_diag=add_self_loops, remove_diag=remove_self_loops,
+                                 transpose=True, device=device)
+    for op in (fwd, bwd):
+        if op is not None and F:
+            op.maybe_build_rbu(F, rbu)
+    return fwd, bwd
+
+
+def _chunk_steps(n_steps: int, bytes_per_step: int) -> int:
+    budget = int(os.environ.get("SGP_B200_CHUNK_BYTES", 4 << 30))
+    return max(1, min(n_steps, budget // max(bytes_per_step, 1)))
+
+
+def sgp_spatial_embedding(x, num_nodes, edge_index, edge_weight=None, k=2, undirected=False,
+                          add_self_loops=False, remove_self_loops=False, bidirectional=False,
+                          one_hot_encoding=False, dropout_rate=0.) -> List[Tensor]:
+    """Reference: lib/sgp_preprocessing.py:163-218.  x [batch, node, features] on CPU or GPU;
+    returns ``[x, Sx, .., S^k x (, reversed-graph hops)]`` on x's device as views of one
+    concatenated buffer."""
+    edge_index, edge_weight = _dropout_edges(edge_index, edge_weight, dropout_rate)
+    dev = _cuda_device_for(x)
+    squeeze = x.dim() == 2
+    x3 = x[None] if squeeze else x
+    B, N, F0 = x3.shape
+    F = F0 + (num_nodes if one_hot_encoding else 0)
+    fwd, bwd = make_operators(edge_index, edge_weight, num_nodes, undirected=undirected,
+                              add_self_loops=add_self_loops, remove_self_loops=remove_self_loops,
+                              bidirectional=bidirectional, device=dev, F=F)
+    nb = spatial_blocks(k, bidirectional)
+    out = torch.empty(B, N, nb * F, dtype=torch.float32, device=x.device)
+    step = _chunk_steps(B, N * nb * F * 4) if not x.is_cuda else B
+    for t0 in range(0, B, step):
+        t1 = min(B, t0 + step)
+        buf = out[t0:t1] if x.is_cuda else torch.empty(t1 - t0, N, nb * F, device=dev)
+        buf[..., :F0] = x3[t0:t1].to(device=dev, dtype=torch.float32)
+        if one_hot_encoding:
+            buf[..., F0:F] = torch.eye(num_nodes, device=dev)
+        propagate_into(buf, F, k, fwd, bwd)
+        if not x.is_cuda:
+            out[t0:t1] = buf.to(x.device)
+    res = [out[..., b * F:(b + 1) * F] for b in range(nb)]
+    return [r[0] for r in res] if squeeze else res
+
+
+def reservoir_preprocessing_(data, hidden_size: int, preprocess_exogenous=False, num_layers=1,
+                             leaking_rate=0.9, spectral_radius=0.9, density=0.9, activation='tanh',
+                             bias=True, cuda=False):
+    """Reference: lib/sgp_preprocessing.py:40-64.  ``cuda`` is accepted and ignored: the scan always
+    runs on the GPU and the result comes back on ``data``'s device, like the reference's
+    ``.to(device)``."""
+    reservoir = Reservoir(input_size=data.size(-1), hidden_size=hidden_size, num_layers=num_layers,
+                          leaking_rate=leaking_rate, spectral_radius=spectral_radius, density=density,
+                          activation=activation, bias=bias)
+    return reservoir(data[None])[0].to(data.device)
+
+
+def preprocess_dataset(dataset, preprocess_exogenous, reservoir_kwargs, sgp_kwargs):
+    """Reference: lib/sgp_preprocessing.py:15-37 (dataset is a tsl SpatioTemporalDataset or anything
+    with the same ``exogenous / get_tensors / edge_index / edge_weight / add_exogenous /
+    set_input_map`` surface)."""
+    if isinstance(preprocess_exogenous, bool):
+        preprocess_exogenous = dataset.exogenous.keys() if preprocess_exogenous else []
+    if not isinstance(preprocess_exogenous, (list, tuple)):
+        preprocess_exogenous = list(preprocess_exogenous) \
+            if not isinstance(preprocess_exogenous, str) else [preprocess_exogenous]
+    data, _ = dataset.get_tensors(['data'] + list(preprocess_exogenous), preprocess=True, cat_dim=-1)
+    res = reservoir_preprocessing_(data, **reservoir_kwargs)
+    res = sgp_spatial_embedding(res, num_nodes=data.size(1), edge_index=dataset.edge_index,
+                                edge_weight=dataset.edge_weight, **sgp_kwargs)
+    dataset.add_exogenous('processed_x', torch.cat(res, -1), add_to_input_map=False)
+    dataset.set_input_map({'x': ['processed_x']})

@@ -1,0 +1,164 @@
+"""Deep leaky echo-state reservoir — host side of kernel K1.
+
+Mirrors the public surface of the reference's ``lib/nn/reservoir/reservoir.py`` (class names,
+constructor arguments, parameter names ``w_ih / w_hh / b_ih``, attribute ``reservoir_layers``,
+``forward(x[b,s,n,f], h0, return_last_state) -> [b,s,n,L*H]``) so encoders, experiment scripts and
+``filter_args`` keep working, but the modules only *hold* the frozen random weights: the recurrence
+itself runs in ``sgp_reservoir_scan`` (csrc/reservoir_scan.cu), one fused launch per layer and time
+chunk, and there is no torch/CPU implementation behind it.
+
+Weight generation stays on the host with torch's CPU generator, in the reference's call order
+(reservoir.py:54-75), so that ``torch.manual_seed(s)`` gives bit-identical weights:
+uniform w_ih, uniform b_ih, uniform w_hh, randperm mask when density < 1, eigvals rescale.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import SgpError
+
+_ALLOWED = ("tanh", "relu", "self_norm", "identity")
+
+
+def _cuda_device_for(t: torch.Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise SgpError("sgp_b200 needs a CUDA device: the encoder has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class ReservoirLayer(nn.Module):
+    """Frozen weights of one reservoir layer (reference: reservoir.py:18-81)."""
+
+    def __init__(self, input_size, hidden_size, spectral_radius, leaking_rate, bias=True, density=1.,
+                 in_scaling=1., bias_scale=1., activation='tanh'):
+        super().__init__()
+        # reference behaviour kept on purpose: the assert admits 'identity', but resolving it through
+        # tsl's get_functional_activation raises (tests/golden/reference_facts.txt)
+        assert activation in _ALLOWED
+        if activation == 'identity':
+            raise ValueError("Activation 'identity' not valid.")
+        self.activation_name = activation
+        self.w_ih_scale = in_scaling
+        self.b_scale = bias_scale
+        self.density = density
+        self.hidden_size = hidden_size
+        self.alpha = leaking_rate
+        self.spectral_radius = spectral_radius
+        self.w_ih = nn.Parameter(torch.empty(hidden_size, input_size), requires_grad=False)
+        self.w_hh = nn.Parameter(torch.empty(hidden_size, hidden_size), requires_grad=False)
+        # `bias=False` still creates a bias in the reference (":47 if bias is not None")
+        if bias is not None:
+            self.b_ih = nn.Parameter(torch.empty(hidden_size), requires_grad=False)
+        else:
+            self.register_parameter('b_ih', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        H = self.hidden_size
+        self.w_ih.data.uniform_(-1, 1).mul_(self.w_ih_scale)
+        if self.b_ih is not None:
+            self.b_ih.data.uniform_(-1, 1).mul_(self.b_scale)
+        self.w_hh.data.uniform_(-1, 1)
+        if self.density < 1:
+            cells = H * H
+            n_zero = int(cells * (1 - self.density))
+            gate = self.w_hh.data.new_ones(cells)
+            gate[torch.randperm(cells)[:n_zero]] = 0.
+            self.w_hh.data.mul_(gate.view(H, H))
+        rho = torch.linalg.eigvals(self.w_hh.data).abs()
+        self.w_hh.data.mul_(self.spectral_radius / torch.max(rho))
+
+    def device_weights(self, device):
+        """(wpack [(FinP+H), H], bias [H]) on `device`, in the kernel's k-major layout."""
+        w_ih = self.w_ih.detach().to(device=device, dtype=torch.float32)
+        w_hh = self.w_hh.detach().to(device=device, dtype=torch.float32)
+        if self.b_ih is not None:
+            b = self.b_ih.detach().to(device=device, dtype=torch.float32).contiguous()
+        else:
+            b = torch.zeros(self.hidden_size, device=device)
+        return ops.reservoir_pack(w_ih, w_hh), b
+
+    def forward(self, x, h):
+        """One step for [N, Fin] / [N, H] tensors (a Tc = 1 scan on the device)."""
+        dev = _cuda_device_for(x)
+        wpack, b = self.device_weights(dev)
+        state = h.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
+        xin = x.detach().to(device=dev, dtype=torch.float32).contiguous()[None]
+        out = torch.empty(1, xin.size(1), self.hidden_size, device=dev)
+        ops.reservoir_scan(xin, wpack, b, self.alpha, self.activation_name, state, out)
+        return out[0].to(x.device)
+
+
+class Reservoir(nn.Module):
+    """Stack of reservoir layers (reference: reservoir.py:84-186)."""
+
+    def __init__(self, input_size, hidden_size, input_scaling=1., num_layers=1, leaking_rate=0.9,
+                 spectral_radius=0.9, density=0.9, activation='tanh', bias=True, alpha_decay=False):
+        super().__init__()
+        self.mode = activation
+        self.input_size = input_size
+        self.input_scaling = input_scaling
+        self.hidden_size = hidden_size
+        self.num_layers = num_layers
+        self.leaking_rate = leaking_rate
+        self.spectral_radius = spectral_radius
+        self.density = density
+        self.bias = bias
+        self.alpha_decay = alpha_decay
+        stack, leak = [], leaking_rate
+        for depth in range(num_layers):
+            # `bias` is deliberately not forwarded: the reference never does (reservoir.py:112-120)
+            stack.append(ReservoirLayer(input_size=hidden_size if depth else input_size,
+                                        hidden_size=hidden_size, in_scaling=input_scaling,
+                                        density=density, activation=activation,
+                                        spectral_radius=spectral_radius, leaking_rate=leak))
+            if alpha_decay:
+                leak = np.clip(leak - 0.1, 0.1, 1.)
+        self.reservoir_layers = nn.ModuleList(stack)
+
+    def reset_parameters(self):
+        for layer in self.reservoir_layers:
+            layer.reset_parameters()
+
+    # ---- device-side execution ------------------------------------------------------------
+    def device_plan(self, device) -> List[tuple]:
+        """[(wpack, bias, alpha)] per layer, uploaded/packed for `device`."""
+        return [(*layer.device_weights(device), float(layer.alpha)) for layer in self.reservoir_layers]
+
+    def scan_chunk(self, plan, x_chunk: torch.Tensor, h_state: torch.Tensor, out: torch.Tensor) -> None:
+        """Advance all layers over one chunk.  x_chunk [Tc,N,Fin] (device), h_state [L,N,H] in/out,
+        out [Tc,N,>=L*H] view: layer l writes features [l*H,(l+1)*H) and reads layer l-1's block."""
+        H = self.hidden_size
+        inp = x_chunk
+        for l, (wpack, b, alpha) in enumerate(plan):
+            blk = out[..., l * H:(l + 1) * H]
+            ops.reservoir_scan(inp, wpack, b, alpha, self.mode, h_state[l], blk)
+            inp = blk
+
+    def forward(self, x, h0=None, return_last_state=False):
+        """x [b, s, n, f] -> [b, s, n, L*H] on x's device (b*n nodes are scanned together)."""
+        B, S, N, Fin = x.size()
+        dev = _cuda_device_for(x)
+        L, H = len(self.reservoir_layers), self.hidden_size
+        plan = self.device_plan(dev)
+        # 'b s n f -> s (b n) f'
+        xd = x.detach().to(device=dev, dtype=torch.float32).permute(1, 0, 2, 3).reshape(S, B * N, Fin)
+        xd = xd.contiguous()
+        if h0 is None:
+            state = torch.zeros(L, B * N, H, device=dev)
+        else:
+            state = h0.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
+        out = torch.empty(S, B * N, L * H, device=dev)
+        self.scan_chunk(plan, xd, state, out)
+        # 's (b n) (l f) -> b s n (l f)'
+        out = out.view(S, B, N, L * H).permute(1, 0, 2, 3)
+        if return_last_state:
+            return out[:, -1].contiguous().to(x.device)
+        return out.contiguous().to(x.device)

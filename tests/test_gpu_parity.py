@@ -1,0 +1,339 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped Python API) against the CPU
+oracle and the reference's golden vectors.  Tolerance: the north_star's 1e-4 relative fp32, as the
+block-wise allclose of SURVEY.md 8(c): |got-ref| <= 1e-4 |ref| + 1e-5 max|ref_block|.
+CSR structure (rowptr / col) must match the oracle bit-for-bit."""
+import numpy as np
+import pytest
+import torch
+
+import sgp_b200
+from oracle import sgp_oracle as O
+from sgp_b200 import _lib, ops
+from sgp_b200.preprocessing import build_operator
+from sgp_b200.synthetic import sensor_knn, sensor_signal, sensor_thresh
+from tests.helpers import golden_names, load_golden, random_graph
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def assert_blocks_close(got, ref, block, rtol=1e-4, atol_rel=1e-5):
+    ok, worst = O.blockwise_allclose(got, ref, block, rtol=rtol, atol_rel=atol_rel)
+    assert ok, f"worst |err|/tol = {worst:.3g}"
+
+
+# ---------------------------------------------------------------- K1 reservoir
+def run_scan(x, layers, act, chunk=None, h0=None):
+    """Drive sgp_reservoir_scan layer by layer exactly like Reservoir.scan_chunk does."""
+    x = torch.as_tensor(x, device=DEV)
+    T, N, _ = x.shape
+    H, L = layers[0]["w_hh"].shape[0], len(layers)
+    out = torch.empty(T, N, L * H, device=DEV)
+    state = torch.zeros(L, N, H, device=DEV) if h0 is None else torch.as_tensor(h0, device=DEV).clone()
+    packs = [(ops.reservoir_pack(l["w_ih"].to(DEV), l["w_hh"].to(DEV)), l["b_ih"].to(DEV)) for l in layers]
+    step = chunk or T
+    for t0 in range(0, T, step):
+        inp = x[t0:t0 + step]
+        for i, (wp, b) in enumerate(packs):
+            blk = out[t0:t0 + step, :, i * H:(i + 1) * H]
+            ops.reservoir_scan(inp, wp, b, layers[i]["alpha"], act, state[i], blk)
+            inp = blk
+    return out.cpu().numpy(), state.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_scan_vs_reference_golden(name):
+    g = load_golden(name)
+    act = g["kwargs"].get("activation", "tanh")
+    y, _ = run_scan(g["x"], g["layers"], act)
+    H = g["kwargs"]["hidden_size"]
+    assert_blocks_close(y, g["y"], H)
+
+
+@pytest.mark.parametrize("H,N,Fin,L,act", [(128, 37, 3, 1, "tanh"), (256, 70, 1, 1, "tanh"),
+                                            (256, 33, 3, 2, "tanh"), (128, 300, 2, 2, "relu"),
+                                            (128, 20, 3, 1, "self_norm"), (256, 9, 2, 1, "identity"),
+                                            (64, 50, 3, 2, "tanh"), (32, 11, 1, 1, "tanh"),
+                                            (20, 13, 5, 2, "tanh")])
+def test_scan_vs_oracle(H, N, Fin, L, act):
+    torch.manual_seed(H + N)
+    layers = O.draw_reservoir(Fin, H, L, 0.9, 0.9, 0.7, 1.0, alpha_decay=(L > 1))
+    x = sensor_signal(40, N, seed=5)[..., :Fin] if Fin <= 3 else \
+        np.random.default_rng(0).standard_normal((40, N, Fin)).astype(np.float32)
+    ref = O.reservoir_states(x, layers, act).numpy()
+    y, _ = run_scan(x, layers, act)
+    assert_blocks_close(y, ref, H)
+
+
+def test_scan_tiled_kernel_sizes():
+    """N large enough to select each node-tile width of the tiled kernel (TM = 8 / 4 / 2)."""
+    for N in (9500, 4800, 700):
+        torch.manual_seed(N)
+        layers = O.draw_reservoir(1, 256, 1, 0.9, 0.9, 0.7)
+        x = sensor_signal(6, N, seed=2, exogenous=False)
+        ref = O.reservoir_states(x, layers, "tanh").numpy()
+        y, _ = run_scan(x, layers, "tanh")
+        assert_blocks_close(y, ref, 256)
+
+
+def test_scan_chunked_equals_unchunked_and_carries_state():
+    torch.manual_seed(3)
+    layers = O.draw_reservoir(3, 128, 2, 0.9, 0.9, 0.7, alpha_decay=True)
+    x = sensor_signal(37, 45, seed=1)
+    full, s_full = run_scan(x, layers, "tanh")
+    part, s_part = run_scan(x, layers, "tanh", chunk=5)
+    np.testing.assert_array_equal(full, part)
+    np.testing.assert_array_equal(s_full, s_part)
+    np.testing.assert_array_equal(s_full[1], full[-1, :, 128:])
+
+
+def test_scan_long_recurrence_stays_in_tolerance():
+    """1000 steps at H=256 against the float64 oracle (the ESN is contractive: no error growth)."""
+    torch.manual_seed(9)
+    layers = O.draw_reservoir(1, 256, 1, 0.9, 0.9, 0.7)
+    x = sensor_signal(1000, 24, seed=4, exogenous=False)
+    ref = O.reservoir_states(x, layers, "tanh", dtype=torch.float64).numpy()
+    y, _ = run_scan(x, layers, "tanh")
+    assert_blocks_close(y[-50:], ref[-50:], 256)
+
+
+def test_scan_closed_forms():
+    # leak 1, W_hh = 0  =>  h_t = tanh(W_ih x_t + b)
+    H, N, Fin = 128, 10, 3
+    g = torch.Generator().manual_seed(0)
+    layer = dict(w_ih=torch.randn(H, Fin, generator=g), w_hh=torch.zeros(H, H),
+                 b_ih=torch.randn(H, generator=g), alpha=1.0)
+    x = torch.randn(7, N, Fin, generator=g)
+    y, _ = run_scan(x.numpy(), [layer], "tanh")
+    want = torch.tanh(x @ layer["w_ih"].t() + layer["b_ih"]).numpy()
+    np.testing.assert_allclose(y, want, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- K3 CSR build
+FLAG_CASES = [dict(), dict(set_diag=True), dict(remove_diag=True), dict(gcn_norm=True, symmetrize=True),
+              dict(set_diag=True, gcn_norm=True, symmetrize=True), dict(transpose=True),
+              dict(transpose=True, set_diag=True)]
+
+
+def oracle_csr(ei, ew, n, set_diag=False, remove_diag=False, gcn_norm=False, symmetrize=False,
+               transpose=False):
+    if transpose:
+        ei = ei[[1, 0]]
+    if symmetrize:
+        ei, ew = O.undirected_edges(ei, ew, n)
+    return O.build_operator(ei, ew, n, gcn_norm=gcn_norm, set_diag=set_diag, remove_diag=remove_diag)
+
+
+@pytest.mark.parametrize("flags", FLAG_CASES)
+@pytest.mark.parametrize("weighted", [True, False])
+def test_csr_build_structure_bit_exact(flags, weighted):
+    n = 61
+    ei, ew = random_graph(n, 700, seed=8, weighted=weighted)        # has duplicates and self loops
+    ei[:, :5] = np.array([[3, 3, 3, 7, 7], [9, 9, 9, 7, 7]])       # forced duplicates + diagonal
+    op = build_operator(torch.from_numpy(ei), None if ew is None else torch.from_numpy(ew), n,
+                        device=DEV, **flags)
+    rowptr, col, val = oracle_csr(ei, ew, n, **flags)
+    np.testing.assert_array_equal(op.csr.rowptr.cpu().numpy(), rowptr)
+    np.testing.assert_array_equal(op.csr.col.cpu().numpy(), col)
+    np.testing.assert_allclose(op.csr.val.cpu().numpy(), val, rtol=2e-6, atol=1e-9)
+
+
+def test_csr_build_edge_cases():
+    # empty edge list; isolated rows; N = 1
+    op = build_operator(torch.zeros(2, 0, dtype=torch.long), None, 5, device=DEV)
+    assert op.csr.nnz == 0 and op.csr.rowptr.tolist() == [0] * 6
+    op = build_operator(torch.zeros(2, 0, dtype=torch.long), None, 3, set_diag=True, device=DEV)
+    assert op.csr.col.tolist() == [0, 1, 2] and op.csr.val.tolist() == [1.0, 1.0, 1.0]
+    ei = torch.tensor([[1, 1, 0], [0, 0, 1]])
+    op = build_operator(ei, torch.tensor([1.0, 3.0, 5.0]), 3, device=DEV)
+    assert op.csr.rowptr.tolist() == [0, 2, 3, 3]
+    np.testing.assert_allclose(op.csr.val.cpu().numpy(), [0.25, 0.75, 1.0])
+    with pytest.raises(_lib.SgpError, match="outside"):
+        build_operator(torch.tensor([[0, 9], [1, 1]]), None, 3, device=DEV)
+    with pytest.raises(RuntimeError, match="Edge index must be"):
+        sgp_b200.preprocess_adj("nope", None, 3)
+
+
+# ---------------------------------------------------------------- K2 SpMM
+@pytest.mark.parametrize("F", [256, 128, 64, 4, 384, 7, 130])
+def test_spmm_csr_vs_oracle(F):
+    n = 83
+    ei, ew = random_graph(n, 900, seed=F)
+    ei = ei[:, ei[1] != 5]                                           # row 5 empty
+    ew = ew[: ei.shape[1]]
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    rowptr, col, val = O.build_operator(ei, ew, n, set_diag=False)
+    x = np.random.default_rng(F).standard_normal((3, n, F)).astype(np.float32)
+    src = torch.from_numpy(x).to(DEV)
+    dst = torch.full_like(src, float("nan"))
+    ops.spmm(op.csr, src, dst)
+    ref = O.spmm(rowptr, col, val, x, impl="c")
+    assert_blocks_close(dst.cpu().numpy(), ref, F)
+    assert float(dst[:, 5].abs().max()) == 0.0
+    # strided views inside a wider buffer + a row schedule
+    buf = torch.zeros(3, n, 3 * F + 4, device=DEV)
+    buf[..., :F] = src
+    order = torch.randperm(n, device=DEV).to(torch.int32)
+    ops.spmm(op.csr, buf[..., :F], buf[..., F:2 * F], row_order=order)
+    assert_blocks_close(buf[..., F:2 * F].cpu().numpy(), ref, F)
+    assert float(buf[..., 2 * F:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("R", [4, 8, 16])
+@pytest.mark.parametrize("F", [128, 256])
+def test_spmm_rbu_vs_oracle(R, F):
+    n, k = 1203, 20                                                   # n not a multiple of R
+    ei, ew = sensor_knn(n, k, seed=R)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    rbu = ops.rbu_build(op.csr, R)
+    assert rbu.fill > 0.3
+    rowptr, col, val = O.build_operator(ei, ew, n, set_diag=False)
+    x = np.random.default_rng(R).standard_normal((2, n, F)).astype(np.float32)
+    buf = torch.zeros(2, n, 2 * F, device=DEV)
+    buf[..., :F] = torch.from_numpy(x).to(DEV)
+    ops.spmm_rbu(rbu, buf[..., :F], buf[..., F:])
+    ref = O.spmm(rowptr, col, val, x, impl="c")
+    assert_blocks_close(buf[..., F:].cpu().numpy(), ref, F)
+    # and it agrees with the CSR kernel to rounding
+    chk = torch.empty(2, n, F, device=DEV)
+    ops.spmm(op.csr, buf[..., :F], chk)
+    np.testing.assert_allclose(buf[..., F:].cpu().numpy(), chk.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_spmm_rbu_irregular_graph_with_duplicates():
+    n = 500
+    ei, ew = random_graph(n, 6000, seed=1)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    rbu = ops.rbu_build(op.csr, 8)
+    x = torch.randn(2, n, 128, device=DEV)
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    ops.spmm_rbu(rbu, x, a)
+    ops.spmm(op.csr, x, b)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_khop_chain_fills_blocks_in_place():
+    n, F, K = 97, 128, 3
+    ei, ew = random_graph(n, 800, seed=2)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    x = np.random.default_rng(0).standard_normal((4, n, F)).astype(np.float32)
+    buf = torch.zeros(4, n, (K + 1) * F, device=DEV)
+    buf[..., :F] = torch.from_numpy(x).to(DEV)
+    ops.khop_spmm(op.csr, buf, 0, 1, K, F)
+    ref = np.concatenate(O.spatial_embedding(x, n, ei, ew, k=K, impl="c"), -1)
+    assert_blocks_close(buf.cpu().numpy(), ref, F)
+    with pytest.raises(_lib.SgpError):
+        ops.khop_spmm(op.csr, buf, 1, 1, K, F)                        # input inside output range
+
+
+def test_row_stochastic_property_full_size_rows():
+    """S 1 = 1 on rows with edges, at a size the oracle is not run on (N = 100k, deg 100)."""
+    n = 100_000
+    ei, ew = sensor_knn(n, 100, seed=0)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    assert op.csr.nnz == n * 100
+    ones = torch.ones(1, n, 128, device=DEV)
+    out = torch.empty_like(ones)
+    ops.spmm(op.csr, ones, out)
+    assert float((out - 1).abs().max()) < 1e-5
+    op.maybe_build_rbu(128, "force16")
+    out2 = torch.empty_like(ones)
+    op.apply(ones, out2)
+    assert float((out2 - 1).abs().max()) < 1e-5
+    # linearity + agreement of the two formats on random data
+    x = torch.randn(1, n, 128, device=DEV)
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    ops.spmm(op.csr, x, a)
+    op.apply(x, b)
+    assert float((a - b).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------- K4 + full encoders
+def test_global_mean_block():
+    x = torch.randn(5, 333, 96, device=DEV)
+    sums = torch.empty(5, 96, device=DEV)
+    ops.node_sum(x, sums)
+    out = torch.empty(5, 333, 96, device=DEV)
+    ops.node_mean_broadcast(sums, 333, out)
+    want = x.mean(1, keepdim=True).expand_as(x)
+    np.testing.assert_allclose(out.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_checksum_and_gather():
+    x = torch.randn(1 << 20, device=DEV)
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.checksum(x, acc)
+    assert abs(float(acc) - float(x.double().sum())) < 1e-6 * x.numel()
+    src = torch.randn(3, 50, 12, device=DEV)
+    idx = torch.tensor([4, 4, 49, 0], dtype=torch.int32, device=DEV)
+    dst = torch.empty(3, 4, 12, device=DEV)
+    ops.gather_rows(src, idx, dst)
+    assert torch.equal(dst, src[:, idx.long()])
+
+
+ENCODER_CASES = [
+    # the METR-LA parity config C1 (N=207, T=288, H=64, K=2) and the paper's sgp_la.yaml variant
+    dict(N=207, T=288, H=64, L=1, K=2, bidir=False, glob=False, undirected=False, loops=False),
+    dict(N=207, T=96, H=64, L=2, K=4, bidir=True, glob=True, undirected=False, loops=False, decay=True),
+    dict(N=120, T=40, H=128, L=1, K=3, bidir=False, glob=True, undirected=True, loops=True),
+    dict(N=150, T=30, H=256, L=1, K=2, bidir=True, glob=False, undirected=False, loops=True),
+    dict(N=90, T=25, H=16, L=3, K=2, bidir=False, glob=False, undirected=False, loops=False, decay=True),
+]
+
+
+@pytest.mark.parametrize("c", ENCODER_CASES)
+@pytest.mark.parametrize("where", ["cpu", "cuda"])
+def test_sgp_encoder_vs_oracle(c, where):
+    ei, ew = sensor_thresh(c["N"], 7 * c["N"], seed=1)
+    x = sensor_signal(c["T"], c["N"], seed=1)
+    torch.manual_seed(2)
+    enc = sgp_b200.SGPEncoder(input_size=3, reservoir_size=c["H"], reservoir_layers=c["L"],
+                              leaking_rate=0.9, spectral_radius=0.9, density=0.7, input_scaling=1.0,
+                              receptive_field=c["K"], bidirectional=c["bidir"],
+                              alpha_decay=c.get("decay", False), global_attr=c["glob"],
+                              add_self_loops=c["loops"], undirected=c["undirected"])
+    enc.chunk_steps = 17                                             # force several chunks
+    xt = torch.from_numpy(x).to(where)
+    y = enc(xt, torch.from_numpy(ei).to(where), torch.from_numpy(ew).to(where))
+    assert y.device.type == where and y.shape == (c["T"], c["N"], enc.output_size)
+    layers = [dict(w_ih=l.w_ih.data, w_hh=l.w_hh.data, b_ih=l.b_ih.data, alpha=l.alpha)
+              for l in enc.reservoir.reservoir_layers]
+    ref = O.sgp_encoder(x, ei, ew, layers, "tanh", c["K"], c["bidir"], c["undirected"], c["glob"],
+                        add_self_loops=c["loops"], impl="c")
+    assert_blocks_close(y.cpu().numpy(), ref, c["L"] * c["H"])
+
+
+def test_spatial_embedding_list_api_and_one_hot():
+    n, F = 40, 8
+    ei, ew = random_graph(n, 200, seed=6)
+    x = np.random.default_rng(1).standard_normal((3, n, F)).astype(np.float32)
+    res = sgp_b200.sgp_spatial_embedding(torch.from_numpy(x), n, torch.from_numpy(ei),
+                                         torch.from_numpy(ew), k=2, bidirectional=True,
+                                         one_hot_encoding=True)
+    ref = O.spatial_embedding(x, n, ei, ew, k=2, bidirectional=True, one_hot_encoding=True, impl="c")
+    assert len(res) == len(ref) == 5
+    for a, b in zip(res, ref):
+        assert a.shape == b.shape and a.device.type == "cpu"
+        assert_blocks_close(a.numpy(), b, F + n)
+    adj = sgp_b200.preprocess_adj(ei, ew, n, set_diag=False)          # numpy input, `adj @ x`
+    y = adj @ torch.from_numpy(x)
+    assert_blocks_close(y.numpy(), ref[1][..., :F], F)
+
+
+def test_temporal_encoder_and_reservoir_module_api():
+    g = load_golden("tanh_l2_decay")
+    kw = dict(g["kwargs"])
+    torch.manual_seed(g["seed"])
+    enc = sgp_b200.SGPTemporalEncoder(input_size=kw["input_size"], reservoir_size=kw["hidden_size"],
+                                      reservoir_layers=kw["num_layers"], leaking_rate=kw["leaking_rate"],
+                                      spectral_radius=kw["spectral_radius"], density=kw["density"],
+                                      input_scaling=kw["input_scaling"], alpha_decay=True)
+    y = enc(torch.from_numpy(g["x"]), None, None)
+    assert_blocks_close(y.numpy(), g["y"], kw["hidden_size"])
+    # Reservoir.forward: [b, s, n, f] with b = 2 (nodes of both batch items scanned together)
+    xb = torch.from_numpy(np.stack([g["x"], g["x"][::-1].copy()]))
+    yb = enc.reservoir(xb)
+    assert yb.shape == (2, *g["y"].shape)
+    assert_blocks_close(yb[0].numpy(), g["y"], kw["hidden_size"])
+    last = enc.reservoir(xb, return_last_state=True)
+    np.testing.assert_array_equal(last.numpy(), yb[:, -1].numpy())

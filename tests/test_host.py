@@ -1,0 +1,175 @@
+"""CPU-only checks of the host layer: ABI surface, weight generation parity with the reference's
+golden weights, API mirror (signatures, argparse hooks, errors), row grouping (host code)."""
+import argparse
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import sgp_b200
+from sgp_b200 import _lib, ops
+from sgp_b200.synthetic import sensor_knn, sensor_signal, sensor_thresh
+from tests.helpers import golden_names, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "sgp_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|int64_t|const char\*)\s+(sgp_[a-z_0-9]+)\(", header, re.M))
+    assert declared, "no declarations found in the header"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/sgp_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.sgp_version() >= 100
+
+
+def test_no_cpu_fallback_product_raises_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    enc = sgp_b200.SGPTemporalEncoder(input_size=1, reservoir_size=8)
+    with pytest.raises(_lib.SgpError):
+        enc(torch.zeros(3, 2, 1))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "sgp_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no CPU", ""), f"sgp_b200/{fn} mentions the oracle"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_weight_init_bit_exact_vs_reference(name):
+    g = load_golden(name)
+    kw = dict(g["kwargs"])
+    torch.manual_seed(g["seed"])
+    res = sgp_b200.Reservoir(**kw)
+    assert len(res.reservoir_layers) == len(g["layers"])
+    for layer, ref in zip(res.reservoir_layers, g["layers"]):
+        assert torch.equal(layer.w_ih.data, ref["w_ih"])
+        assert torch.equal(layer.w_hh.data, ref["w_hh"])
+        assert torch.equal(layer.b_ih.data, ref["b_ih"])
+        assert float(layer.alpha) == ref["alpha"]
+        assert not layer.w_hh.requires_grad
+
+
+def test_reference_quirks_kept():
+    with pytest.raises(ValueError):                       # tests/golden/reference_facts.txt
+        sgp_b200.Reservoir(1, 4, activation="identity")
+    with pytest.raises(AssertionError):
+        sgp_b200.Reservoir(1, 4, activation="gelu")
+    layer = sgp_b200.ReservoirLayer(2, 4, 0.9, 0.9, bias=False)
+    assert layer.b_ih is not None                         # reservoir.py:47 `bias is not None`
+
+
+def test_constructor_signatures_match_reference():
+    want = {
+        sgp_b200.SGPEncoder: ['input_size', 'reservoir_size', 'reservoir_layers', 'leaking_rate',
+                              'spectral_radius', 'density', 'input_scaling', 'receptive_field',
+                              'bidirectional', 'alpha_decay', 'global_attr', 'add_self_loops',
+                              'undirected', 'reservoir_activation'],
+        sgp_b200.SGPSpatialEncoder: ['receptive_field', 'bidirectional', 'undirected', 'global_attr',
+                                     'add_self_loops'],
+        sgp_b200.SGPTemporalEncoder: ['input_size', 'reservoir_size', 'reservoir_layers',
+                                      'leaking_rate', 'spectral_radius', 'density', 'input_scaling',
+                                      'alpha_decay', 'reservoir_activation'],
+        sgp_b200.Reservoir: ['input_size', 'hidden_size', 'input_scaling', 'num_layers',
+                             'leaking_rate', 'spectral_radius', 'density', 'activation', 'bias',
+                             'alpha_decay'],
+    }
+    for cls, names in want.items():
+        assert inspect.getfullargspec(cls.__init__).args[1:] == names, cls
+    sig = inspect.signature(sgp_b200.sgp_spatial_embedding)
+    assert list(sig.parameters) == ['x', 'num_nodes', 'edge_index', 'edge_weight', 'k', 'undirected',
+                                    'add_self_loops', 'remove_self_loops', 'bidirectional',
+                                    'one_hot_encoding', 'dropout_rate']
+    assert sig.parameters['k'].default == 2
+    sig = inspect.signature(sgp_b200.preprocess_adj)
+    assert list(sig.parameters) == ['edge_index', 'edge_weight', 'num_nodes', 'gcn_norm', 'set_diag',
+                                    'remove_diag']
+    assert sig.parameters['set_diag'].default is True
+    sig = inspect.signature(sgp_b200.encode_dataset)
+    assert list(sig.parameters) == ['dataset', 'encoder_class', 'encoder_kwargs', 'encode_exogenous',
+                                    'keep_raw', 'save_path']
+
+
+@pytest.mark.parametrize("cls", [sgp_b200.SGPEncoder, sgp_b200.SGPSpatialEncoder,
+                                 sgp_b200.SGPTemporalEncoder])
+def test_argparse_hook(cls):
+    p = cls.add_model_specific_args(argparse.ArgumentParser())
+    ns = p.parse_args(['--receptive-field', '3', '--bidirectional', 'true'])
+    assert ns.receptive_field == 3 and ns.bidirectional is True and ns.global_attr is False
+
+
+def test_output_size_and_block_count():
+    torch.manual_seed(0)
+    enc = sgp_b200.SGPEncoder(3, 64, 2, 0.9, 0.9, 0.7, 1.0, 4, True, True, True)
+    assert enc.output_size == 1280          # config/traffic/sgp_la.yaml: (1+4*2+1)*2*64
+    assert enc.sgp_encoder.num_blocks() == 10
+
+
+def test_bad_edge_index_type_raises_runtime_error():
+    with pytest.raises(RuntimeError, match="Edge index must be"):
+        sgp_b200.preprocess_adj([[0], [1]], None, 2)
+
+
+def test_encode_dataset_nonbool_exogenous_is_nameerror():
+    class D:
+        exogenous = {}
+    with pytest.raises(NameError):
+        sgp_b200.encode_dataset(D(), sgp_b200.SGPTemporalEncoder, {}, encode_exogenous=["u"])
+
+
+# ---- host-side row grouping (pure CPU code inside the .so) ---------------------------------
+def _csr_from_edges(ei, w, n):
+    import scipy.sparse as sp
+    A = sp.csr_matrix((w, (ei[1], ei[0])), shape=(n, n))
+    A.sort_indices()
+    return A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float32)
+
+
+@pytest.mark.parametrize("R", [4, 8, 16])
+def test_group_rows_is_a_partition_and_compresses_knn(R):
+    n, k = 3000, 24
+    ei, w = sensor_knn(n, k, seed=3)
+    rowptr, col, val = _csr_from_edges(ei, w, n)
+    g = ops.group_rows_host(rowptr, col, val, n, R)
+    assert g.shape == ((n + R - 1) // R, R)
+    rows = g[g >= 0]
+    assert rows.size == n and np.unique(rows).size == n
+    grp = np.empty(n, np.int64)
+    grp[g.reshape(-1)[g.reshape(-1) >= 0]] = (np.arange(g.size) // R)[g.reshape(-1) >= 0]
+    e_rows = np.repeat(np.arange(n), np.diff(rowptr))
+    union = np.unique(grp[e_rows] * n + col).size
+    assert union < 0.75 * len(col)          # neighbours are shared inside groups
+
+
+def test_group_rows_edge_cases():
+    # empty graph, graph with empty rows, N not a multiple of R
+    g = ops.group_rows_host(np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32), 0, 4)
+    assert g.shape == (0, 4)
+    rowptr = np.array([0, 0, 2, 2, 3, 3], np.int32)
+    col = np.array([0, 3, 1], np.int32)
+    val = np.ones(3, np.float32)
+    g = ops.group_rows_host(rowptr, col, val, 5, 4)
+    assert g.shape == (2, 4) and sorted(g[g >= 0].tolist()) == [0, 1, 2, 3, 4]
+    assert (g == -1).sum() == 3
+
+
+def test_synthetic_generators_shapes():
+    ei, w = sensor_knn(500, 10, seed=0)
+    assert ei.shape == (2, 5000) and w.shape == (5000,) and ei.dtype == np.int64
+    assert np.all(np.bincount(ei[1], minlength=500) == 10)       # exactly k entries per ROW
+    assert not np.any(ei[0] == ei[1])
+    ei, w = sensor_thresh(207, 1515, seed=0)
+    assert abs(ei.shape[1] - 1515) < 60 and w.min() > 0.1
+    x = sensor_signal(50, 7)
+    assert x.shape == (50, 7, 3) and x.dtype == np.float32
+    np.testing.assert_allclose(x[:, 0, 1], x[:, 3, 1])             # exogenous broadcast over nodes
