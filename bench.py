@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the SGP training-free encoder on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c4_100k] [--impl reference]
+
+A "step" is one full pass of the encoder hot path (reservoir scan + K-hop propagation) over the
+whole synthetic series of the workload; the output (hundreds of GB at the BASELINE shapes) is
+streamed through a ring of device chunk buffers into a checksum kernel.  Prints ONE JSON line
+(rank 0).  Keys are documented in DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "encoder node-timesteps/sec"
+UNIT = "node-timesteps/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)",
+                    sm_max_mhz=float(p.get("sm_max_mhz", 1965.0)))
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)", sm_max_mhz=1965.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                              ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def workload(name: str):
+    from sgp_b200.synthetic import CONFIGS
+    if name not in CONFIGS:
+        raise SystemExit(f"unknown workload {name}; choose from {list(CONFIGS)}")
+    return dict(CONFIGS[name], name=name)
+
+
+def make_inputs(cfg, T=None, shard=None):
+    from sgp_b200.synthetic import make_graph, sensor_signal
+    ei, ew = make_graph(cfg, seed=0)
+    x = sensor_signal(T or cfg["T"], cfg["N"], seed=1, exogenous=cfg["Fin"] == 3)
+    return ei, ew, x
+
+
+def make_encoder(cfg):
+    import sgp_b200
+    torch.manual_seed(2)
+    return sgp_b200.SGPEncoder(input_size=cfg["Fin"], reservoir_size=cfg["H"], reservoir_layers=1,
+                               leaking_rate=0.9, spectral_radius=0.9, density=0.7, input_scaling=1.0,
+                               receptive_field=cfg["K"], bidirectional=False, alpha_decay=False,
+                               global_attr=False)
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (a port — the reference is Python over torch +
+# torch_sparse, and torch_sparse is not installable here) on the host cores.
+# --------------------------------------------------------------------------------------------
+def cpu_encode_once(cfg, ei, ew, x, layers):
+    from oracle import sgp_oracle as O
+    t0 = time.perf_counter()
+    h = O.reservoir_states(x, layers, "tanh")
+    t1 = time.perf_counter()
+    rowptr, col, val = O.build_operator(ei, ew, cfg["N"], set_diag=False)
+    t2 = time.perf_counter()
+    F = h.shape[-1]
+    out = torch.empty(h.shape[0], cfg["N"], (cfg["K"] + 1) * F)
+    out[..., :F] = h
+    for k in range(cfg["K"]):
+        O.spmm_c(rowptr, col, val, out[..., k * F:(k + 1) * F], out=out[..., (k + 1) * F:(k + 2) * F])
+    t3 = time.perf_counter()
+    return dict(total=t3 - t0, reservoir=t1 - t0, graph=t2 - t1, spmm=t3 - t2,
+                checksum=float(out[-1].double().sum()))
+
+
+def cpu_sample_steps(cfg):
+    """Time steps of the CPU sample: ~10-30 s of CPU work per run of a few steps."""
+    per_step = cfg["N"] * (2 * cfg["H"] * cfg["H"] / 60e9 + 2 * cfg["K"] * cfg.get("k", 8) * cfg["H"] / 10e9)
+    return int(max(2, min(cfg["T"], 5.0 / max(per_step, 1e-9))))
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import sgp_oracle as O
+    O.build_c()
+    torch.set_num_threads(os.cpu_count() or 1)
+    Ts = cpu_sample_steps(cfg)
+    ei, ew, x = make_inputs(cfg, T=Ts)
+    enc = make_encoder(cfg)
+    layers = [dict(w_ih=l.w_ih.data, w_hh=l.w_hh.data, b_ih=l.b_ih.data, alpha=l.alpha)
+              for l in enc.reservoir.reservoir_layers]
+    for _ in range(args.warmup):
+        cpu_encode_once(cfg, ei, ew, x, layers)
+    times = [cpu_encode_once(cfg, ei, ew, x, layers) for _ in range(args.steps)]
+    sec = sum(t["total"] for t in times) / len(times)
+    value = cfg["N"] * Ts / sec
+    cores = max(torch.get_num_threads(), O.c_threads())
+    sample = (f"{Ts} of {cfg['T']} time steps of the same workload (full N/H/K and graph); "
+              f"reservoir {times[-1]['reservoir']:.2f}s + adjacency {times[-1]['graph']:.2f}s + "
+              f"K-hop SpMM {times[-1]['spmm']:.2f}s per step")
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                config=config_dict(cfg, args.gpus, extra=dict(cpu_sample_steps=Ts)),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+def config_dict(cfg, n_gpus, extra=None):
+    d = dict(workload=f"{cfg['name']}: synthetic sensor graph N={cfg['N']}, "
+                      f"{'k=%d-NN' % cfg['k'] if cfg['graph'] == 'knn' else 'thresholded kernel'}, "
+                      f"T={cfg['T']}, H={cfg['H']}, K={cfg['K']}, Fin={cfg['Fin']}, L=1, directed D^-1 A",
+             N=cfg["N"], T=cfg["T"], H=cfg["H"], K=cfg["K"], Fin=cfg["Fin"],
+             l2_policy="inputs larger than L2 (each step streams the whole series; no flush needed)",
+             parallelism=f"rows{n_gpus}" if n_gpus > 1 else "single")
+    if extra:
+        d.update(extra)
+    return d
+
+
+# --------------------------------------------------------------------------------------------
+# own arm
+# --------------------------------------------------------------------------------------------
+class Timed:
+    """CUDA-event pairs around individual launches on the current stream."""
+
+    def __init__(self):
+        self.pairs = {}
+
+    def wrap(self, key, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        self.pairs.setdefault(key, []).append((a, b))
+
+    def summary(self):
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.pairs.items()}
+
+
+def run_own(args, cfg):
+    import sgp_b200
+    from sgp_b200 import _lib, ops
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    if world > 1:
+        from sgp_b200 import sharded
+        return sharded.bench(args, cfg, rank, world, dev, peaks, config_dict, METRIC, UNIT)
+
+    N, T, H, K, Fin = cfg["N"], cfg["T"], cfg["H"], cfg["K"], cfg["Fin"]
+    F, D = H, (K + 1) * H
+    ei, ew, x = make_inputs(cfg)
+    enc = make_encoder(cfg)
+    enc.chunk_steps = args.chunk or max(1, min(T, (args.chunk_mb << 20) // (N * D * 4)))
+    step_T = enc.chunk_steps
+
+    # ---- resident inputs for the device-timed number ---------------------------------------
+    x_dev = torch.from_numpy(x).to(dev)
+    ei_dev, ew_dev = torch.from_numpy(ei).to(dev), torch.from_numpy(ew).to(dev)
+    fwd, bwd = enc.sgp_encoder.build_operators(ei_dev, ew_dev, N, dev, F)
+    plan = enc.reservoir.device_plan(dev)
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    bufs = [torch.empty(step_T, N, D, device=dev) for _ in range(2)]
+    state = torch.zeros(1, N, H, device=dev)
+
+    def one_pass(timed=None):
+        state.zero_()
+        for i, t0 in enumerate(range(0, T, step_T)):
+            t1 = min(T, t0 + step_T)
+            buf = bufs[i % 2][: t1 - t0]
+            if timed is None:
+                enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf)
+                enc.sgp_encoder.encode_chunk(buf, F, fwd, bwd)
+            else:
+                timed.wrap("scan", lambda: enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf))
+                for h in range(1, K + 1):
+                    timed.wrap(("spmm", t1 - t0), lambda h=h: fwd.apply(buf[..., (h - 1) * F:h * F],
+                                                                        buf[..., h * F:(h + 1) * F]))
+            ops.checksum(buf, acc)
+
+    for _ in range(args.warmup):
+        one_pass()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    timed = Timed()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        one_pass(timed)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    value = N * T / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (the hop SpMM) ------------------------------------
+    summ = timed.summary()
+    nnz = fwd.csr.nnz
+    spmm_ms = sum(ms for k, (n, ms) in summ.items() if k != "scan")
+    spmm_n = sum(n for k, (n, ms) in summ.items() if k != "scan")
+    full_key = ("spmm", step_T)
+    n_full, ms_full = summ.get(full_key, (0, 0.0))
+    bytes_per_launch = 8 * nnz + 4 * (N + 1) + 2 * step_T * N * F * 4
+    flops_per_launch = 2 * nnz * F * step_T
+    avg_ms = ms_full / max(n_full, 1)
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+    scan_n, scan_ms = summ.get("scan", (0, 0.0))
+    scan_flops = N * T * (2 * H * (Fin + H) + 6 * H) * args.steps
+    fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    roofline = dict(bound="hbm", kernel="spmm_rbu_kernel<16>" if fwd.rbu is not None else "spmm_csr_vec",
+                    achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
+                    peak_source=peaks["source"], traffic=None,
+                    algorithmic_bytes_per_launch=bytes_per_launch, timesteps_per_launch=step_T,
+                    avg_launch_ms=avg_ms, launches_timed=n_full,
+                    gflops=flops_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0,
+                    fp32_fma_peak_tflops=fma_peak,
+                    share_of_step=spmm_ms / (spmm_ms + scan_ms) if spmm_ms + scan_ms else None)
+    reservoir = dict(kernel="reservoir_scan_tiled", ms_per_step=scan_ms / args.steps,
+                     tflops=scan_flops / (scan_ms * 1e-3) / 1e12 if scan_ms else 0.0,
+                     frac_of_fp32_fma_peak=(scan_flops / (scan_ms * 1e-3) / 1e12) / fma_peak if scan_ms else 0.0,
+                     share_of_step=scan_ms / (spmm_ms + scan_ms) if spmm_ms + scan_ms else None)
+
+    # ---- end to end through the public API with HOST buffers -------------------------------
+    x_pin = torch.from_numpy(x).pin_memory()
+    ei_h, ew_h = torch.from_numpy(ei), torch.from_numpy(ew)
+    host_sum = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def e2e_pass():
+        acc.zero_()
+        enc.encode_stream(x_pin, ei_h, ew_h, lambda t0, t1, chunk: ops.checksum(chunk, acc), device=dev)
+        host_sum.copy_(acc, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(host_sum)
+
+    e2e_pass()
+    t_e2e = []
+    for _ in range(max(1, min(args.steps, 3))):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        chk = e2e_pass()
+        t_e2e.append(time.perf_counter() - t0)
+    e2e_s = sum(t_e2e) / len(t_e2e)
+    h2d = x.nbytes + ei.nbytes + ew.nbytes
+    d2h = 8 + (4 * (N + 1) + 8 * nnz if fwd.rbu is not None else 0)
+    e2e = dict(value=N * T / e2e_s, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+               ms_per_step=e2e_s * 1e3, checksum=chk,
+               note="SGPEncoder.encode_stream on pinned host x + host edge list: H2D of inputs, operator "
+                    "build (CSR + row grouping), scan + K hops, per-chunk checksum, D2H of the checksum; "
+                    "the [T,N,D] output itself (%.0f GB) is not copied back" % (N * T * D * 4 / 1e9))
+
+    # ---- CPU baseline on a bounded sample ---------------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        from oracle import sgp_oracle as O
+        O.build_c()
+        torch.set_num_threads(os.cpu_count() or 1)
+        Ts = cpu_sample_steps(cfg)
+        layers = [dict(w_ih=l.w_ih.data, w_hh=l.w_hh.data, b_ih=l.b_ih.data, alpha=l.alpha)
+                  for l in enc.reservoir.reservoir_layers]
+        cpu_encode_once(cfg, ei, ew, x[:Ts], layers)
+        r = cpu_encode_once(cfg, ei, ew, x[:Ts], layers)
+        cpu = dict(value=N * Ts / r["total"], unit=UNIT, cores=max(torch.get_num_threads(), O.c_threads()),
+                   kind="port",
+                   sample=f"first {Ts} of {T} time steps, full N/H/K/graph: reservoir {r['reservoir']:.2f}s "
+                          f"(torch CPU, same ops as the reference) + adjacency {r['graph']:.2f}s + K-hop SpMM "
+                          f"{r['spmm']:.2f}s (C/OpenMP restatement of torch_sparse spmm)")
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=config_dict(cfg, 1, extra=dict(chunk_steps=step_T, rbu_R=fwd.rbu.R if fwd.rbu else 0,
+                                                      rbu_fill=round(fwd.rbu.fill, 3) if fwd.rbu else None)),
+                roofline=roofline, reservoir=reservoir, cpu_baseline=cpu, e2e=e2e, clocks=clocks,
+                gpu_launches=int(launches), checksum=float(acc))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="c4_100k")
+    ap.add_argument("--chunk", type=int, default=0, help="time steps per chunk (0 = from --chunk-mb)")
+    ap.add_argument("--chunk-mb", type=int, default=8192)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    cfg = workload(args.workload)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_own(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,10 +78,10 @@ __global__ void csr_finalize_structure(const uint64_t* __restrict__ keys, const 
 
 // deg[i] = sum of row i (stored order); s[i] = deg^-1 or deg^-1/2 with inf -> 0
 __global__ void csr_degree_scale(const int32_t* __restrict__ rowptr, const float* __restrict__ w,
-                                 int32_t N, int gcn, float* __restrict__ s) {
+                                 int32_t N, int gcn, int unit_w, float* __restrict__ s) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         float d = 0.f;
-        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) d += w[e];
+        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) d += unit_w ? 1.f : w[e];
         float v = gcn ? (1.0f / sqrtf(d)) : (1.0f / d);
         if (isinf(v)) v = 0.f;
         s[i] = v;
@@ -90,13 +90,13 @@ __global__ void csr_degree_scale(const int32_t* __restrict__ rowptr, const float
 
 __global__ void csr_apply_scale(const uint64_t* __restrict__ keys, const float* __restrict__ w,
                                 const float* __restrict__ s, const CsrCounters* ctr, int32_t N,
-                                int gcn, float* __restrict__ val) {
+                                int gcn, int unit_w, float* __restrict__ val) {
     const int nnz = ctr->nnz;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz;
          e += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t k = keys[e];
         const int r = (int)(k / (uint64_t)N), c = (int)(k % (uint64_t)N);
-        float v = s[r] * w[e];
+        float v = s[r] * (unit_w ? 1.f : w[e]);
         if (gcn) v = v * s[c];
         val[e] = v;
     }
@@ -205,9 +205,11 @@ extern "C" int sgp_csr_build(const int64_t* edge_src, const int64_t* edge_dst, c
     SGP_LAUNCH_CHECK("csr_finalize_structure");
     if (P > 0) {
         const int gcn = (flags & SGP_CSR_GCN_NORM) ? 1 : 0;
-        csr_degree_scale<<<grid_for(N), threads, 0, st>>>(rowptr, w, N, gcn, scale);
+        // to_undirected without edge weights only de-duplicates: every distinct edge counts once
+        const int unit_w = (!weight && (flags & SGP_CSR_SYMMETRIZE)) ? 1 : 0;
+        csr_degree_scale<<<grid_for(N), threads, 0, st>>>(rowptr, w, N, gcn, unit_w, scale);
         SGP_LAUNCH_CHECK("csr_degree_scale");
-        csr_apply_scale<<<grid_for(P), threads, 0, st>>>(keys, w, scale, ctr, N, gcn, val);
+        csr_apply_scale<<<grid_for(P), threads, 0, st>>>(keys, w, scale, ctr, N, gcn, unit_w, val);
         SGP_LAUNCH_CHECK("csr_apply_scale");
     }
     CsrCounters host{};
