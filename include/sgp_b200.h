@@ -76,8 +76,9 @@ int sgp_csr_build(const int64_t* edge_src, const int64_t* edge_dst, const float*
  * ReservoirLayer.forward (:77-81):
  *     h' = (1-alpha) h + alpha * act( x_t W_ih^T + b + h W_hh^T )
  * for every node n and step t of the chunk; h' is written to out[t, n, 0:H] and carried.
- *   wpack   [(FinP + H), H] with FinP = Fin rounded up to a multiple of 4: rows 0..Fin-1 = W_ih^T,
- *           rows Fin..FinP-1 = 0, rows FinP.. = W_hh^T  (made by sgp_reservoir_pack)
+ *   wpack   [sgp_reservoir_pack_rows(Fin, H), H] = [(FinP + H), H], FinP = Fin zero-padded to the
+ *           kernel's k-tile: rows 0..Fin-1 = W_ih^T, rows Fin..FinP-1 = 0, rows FinP.. = W_hh^T
+ *           (made by sgp_reservoir_pack)
  *   h_state [N, H] in/out: state before the first / after the last step of the chunk
  *   x       element (t, n, f) at x[t*x_t_stride + n*x_n_stride + f]
  *   out     element (t, n, j) at out[t*out_t_stride + n*out_n_stride + j]  (a feature block of
@@ -86,6 +87,7 @@ int sgp_csr_build(const int64_t* edge_src, const int64_t* edge_dst, const float*
  * H in {128, 256} with 16-byte aligned out / h_state / wpack and strides % 4 == 0 runs the tiled
  * FFMA2 kernel; every other shape runs the generic (still CUDA) kernel.
  * ------------------------------------------------------------------------------------------- */
+int sgp_reservoir_pack_rows(int Fin, int H);
 int sgp_reservoir_pack(const float* w_ih /*[H,Fin]*/, const float* w_hh /*[H,H]*/, int Fin, int H,
                        float* wpack /*[(FinP+H),H]*/, void* stream);
 int sgp_reservoir_scan(const float* x, int64_t x_t_stride, int64_t x_n_stride, int Fin,

@@ -23,6 +23,7 @@ SIGNATURES = {
     "sgp_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int]),
     "sgp_csr_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int, c_void_p, c_void_p,
                               c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sgp_reservoir_pack_rows": (c_int, [c_int, c_int]),
     "sgp_reservoir_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sgp_reservoir_scan": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_float,
                                    c_float, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,

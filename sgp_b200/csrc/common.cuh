@@ -51,6 +51,13 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
 }
+// gathered rows are used once per warp: read-only path, do not allocate in L1
+__device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 // streaming store (written once, consumed by a later kernel / the host): do not keep in L1
 __device__ __forceinline__ void st_f4(float* p, float4 v) {
     *reinterpret_cast<float4*>(p) = v;

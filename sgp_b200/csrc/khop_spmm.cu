@@ -15,6 +15,8 @@
 //     L2->SM gather traffic by ~R*deg/U and is the path used on kNN sensor graphs.
 // Bound: HBM nominally (bytes/hop = 8 nnz + 4(N+1) + 8 N F Tc), but at deg 100 / F 256 the fp32
 // FMA pipe (2 nnz F flops) and the L2->SM gather traffic are the tighter limits; see DESIGN.md.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sgp {
@@ -181,6 +183,123 @@ spmm_rbu_kernel(const int32_t* __restrict__ grp_ptr, const int32_t* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RBU v2: CTA = one group x TSPAN time steps.  The group's slab (union columns + dense [U, R]
+// values, a contiguous range of the operator arrays) is staged ONCE per CTA in shared memory
+// with cp.async; warp w owns feature chunk (w % nfc) and walks time steps (w / nfc), +tpb, ...
+// Per union column a lane then issues only ONE long-latency load (its float4 of the gathered
+// source row); column ids and values come from shared memory as warp-broadcast LDS.  Gathers
+// are software-pipelined four columns ahead (explicit A/B register buffers) so that ~8 x 512 B
+// are in flight per warp while the previous quad's 128 FFMA2 issue.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRbuPiece = 256;   // union columns staged per pass (R=16: 16 KB values + 1 KB ids)
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+}
+
+// acc[r] += a[r] * x for the R rows of one union column; the column's R values are already in
+// registers (`cur`), the NEXT column's values are fetched from shared memory into `nxt` first so
+// that the LDS latency hides behind this column's 2R FFMA2.
+template <int R>
+__device__ __forceinline__ void rbu_fma_col(float2 (&acc)[R][2], float4 (&cur)[R / 4],
+                                            const float* __restrict__ next_av, const float4& x) {
+    float4 nxt[R / 4];
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k) nxt[k] = *reinterpret_cast<const float4*>(next_av + 4 * k);
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k) {
+        fma4(acc[4 * k + 0][0], acc[4 * k + 0][1], cur[k].x, x);
+        fma4(acc[4 * k + 1][0], acc[4 * k + 1][1], cur[k].y, x);
+        fma4(acc[4 * k + 2][0], acc[4 * k + 2][1], cur[k].z, x);
+        fma4(acc[4 * k + 3][0], acc[4 * k + 3][1], cur[k].w, x);
+    }
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k) cur[k] = nxt[k];
+}
+
+template <int R, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+spmm_rbu_v2(const int32_t* __restrict__ grp_ptr, const int32_t* __restrict__ grp_rows,
+            const int32_t* __restrict__ ucol, const float* __restrict__ uval,
+            int nfc, int tpb, int tspan,
+            const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
+            float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int Tc) {
+    __shared__ __align__(16) float s_val[(kRbuPiece + 1) * R];   // +1 row: the look-ahead read
+    __shared__ __align__(16) int s_col[kRbuPiece];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthr = blockDim.x;
+    const int g = blockIdx.x;
+    const int fc = warp % nfc, tl = warp / nfc;
+    const int t_begin = blockIdx.y * tspan, t_end = min(Tc, t_begin + tspan);
+    const int beg = grp_ptr[g], end = grp_ptr[g + 1];
+    const int foff = fc * 128 + lane * 4;
+
+    for (int t0 = t_begin; t0 < t_end; t0 += tpb) {
+        const int t = t0 + tl;
+        const bool live = t < t_end;
+        const float* sp = src + (size_t)(live ? t : t_begin) * s_ts + foff;
+        float2 acc[R][2];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+
+        for (int p0 = beg; p0 < end; p0 += kRbuPiece) {
+            const int cnt = min(kRbuPiece, end - p0);
+            // a single piece (the common case) stays resident for all time steps of the CTA
+            if (t0 == t_begin || end - beg > kRbuPiece) {
+                __syncthreads();
+                for (int i = tid; i < cnt * (R / 4); i += nthr)
+                    cp_async16(s_val + i * 4, uval + (size_t)p0 * R + i * 4);
+                for (int i = tid; i < cnt; i += nthr) cp_async4(s_col + i, ucol + p0 + i);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+            }
+            if (!live) continue;
+            const int nq = cnt >> 2;
+            float4 a_cur[R / 4];
+#pragma unroll
+            for (int k = 0; k < R / 4; ++k) a_cur[k] = *reinterpret_cast<const float4*>(s_val + 4 * k);
+            float4 xa[4], xb[4];
+            auto gather = [&](float4 (&x)[4], int q) {
+                const int4 c = *reinterpret_cast<const int4*>(s_col + 4 * q);
+                x[0] = ldg_f4_stream(sp + (size_t)c.x * s_ns);
+                x[1] = ldg_f4_stream(sp + (size_t)c.y * s_ns);
+                x[2] = ldg_f4_stream(sp + (size_t)c.z * s_ns);
+                x[3] = ldg_f4_stream(sp + (size_t)c.w * s_ns);
+            };
+            auto compute = [&](const float4 (&x)[4], int q) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rbu_fma_col<R>(acc, a_cur, s_val + (size_t)(4 * q + j + 1) * R, x[j]);
+            };
+            int q = 0;
+            if (nq > 0) gather(xa, 0);
+            for (; q + 2 <= nq; q += 2) {
+                gather(xb, q + 1);
+                compute(xa, q);
+                if (q + 2 < nq) gather(xa, q + 2);
+                compute(xb, q + 1);
+            }
+            if (q < nq) compute(xa, q);
+            for (int j = nq * 4; j < cnt; ++j) {
+                const float4 x = ldg_f4_stream(sp + (size_t)s_col[j] * s_ns);
+                rbu_fma_col<R>(acc, a_cur, s_val + (size_t)(j + 1) * R, x);
+            }
+        }
+        if (live) {
+            float* dp = dst + (size_t)t * d_ts + foff;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int row = __ldg(grp_rows + (size_t)g * R + r);
+                if (row >= 0)
+                    st_f4(dp + (size_t)row * d_ns,
+                          make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y));
+            }
+        }
+    }
+}
+
 static int check_views(const char* who, const void* src, int64_t s_ts, int64_t s_ns, const void* dst,
                        int64_t d_ts, int64_t d_ns, int F) {
     SGP_REQUIRE(src && dst, SGP_EINVAL, "%s: null src/dst", who);
@@ -260,6 +379,27 @@ extern "C" int sgp_spmm_rbu(const int32_t* grp_ptr, const int32_t* grp_rows, con
     if (n_groups == 0 || Tc == 0) return SGP_OK;
     cudaStream_t st = as_stream(stream);
     const int nfc = F / 128;
+    const int version = getenv("SGP_B200_RBU_KERNEL") ? atoi(getenv("SGP_B200_RBU_KERNEL")) : 2;
+    const int tspan_env = getenv("SGP_B200_RBU_TSPAN") ? atoi(getenv("SGP_B200_RBU_TSPAN")) : 0;
+    if (version == 2 && nfc <= 4) {
+        const int tpb = 4 / nfc >= 1 ? 4 / nfc : 1;          // 4 warps per CTA (nfc = 3 -> 1 step, 3 warps)
+        int tspan = tspan_env > 0 ? tspan_env : tpb;         // one time step per warp: t-major order keeps the gathered panel L2-hot
+        tspan = ((tspan + tpb - 1) / tpb) * tpb;
+        const int ny = (Tc + tspan - 1) / tspan;
+        SGP_REQUIRE(ny <= 65535, SGP_EUNSUPPORTED, "sgp_spmm_rbu: Tc=%d too large for one launch", Tc);
+        const int minb = getenv("SGP_B200_RBU_MINB") ? atoi(getenv("SGP_B200_RBU_MINB")) : 4;
+#define SGP_RBU2(RR, MB)                                                                         \
+    spmm_rbu_v2<RR, MB><<<dim3((unsigned)n_groups, ny), nfc * tpb * 32, 0, st>>>(                \
+        grp_ptr, grp_rows, ucol, uval, nfc, tpb, tspan, src, src_t_stride, src_n_stride, dst,    \
+        dst_t_stride, dst_n_stride, Tc)
+        if (R == 4) SGP_RBU2(4, 4);
+        else if (R == 8) SGP_RBU2(8, 4);
+        else if (minb == 3) SGP_RBU2(16, 3);
+        else SGP_RBU2(16, 4);
+#undef SGP_RBU2
+        SGP_LAUNCH_CHECK("spmm_rbu_v2");
+        return SGP_OK;
+    }
     const long long total = (long long)Tc * n_groups * nfc;
     const long long blocks = (total + kSpmmWarps - 1) / kSpmmWarps;
     SGP_REQUIRE(blocks < (1ll << 31), SGP_EUNSUPPORTED, "sgp_spmm_rbu: too many warps for one launch");

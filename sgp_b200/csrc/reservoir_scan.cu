@@ -23,8 +23,14 @@ namespace sgp {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = 8;
-constexpr int kKC = 16;      // W^T rows per pipeline chunk
+constexpr int kKC = 32;      // W^T rows per pipeline chunk
 constexpr int kStages = 3;
+constexpr int kSmallFin = 8; // Fin <= 8: input projection done in registers, outside the W pipeline
+
+// rows of W_ih^T in the packed weight matrix (zero padded): see sgp_reservoir_pack_rows()
+__host__ __device__ inline int fin_padded(int Fin) {
+    return Fin <= kSmallFin ? ((Fin + 3) & ~3) : ((Fin + kKC - 1) / kKC) * kKC;
+}
 
 __device__ __forceinline__ float activate(float v, int act) {
     if (act == SGP_ACT_TANH) return tanhf(v);
@@ -42,7 +48,11 @@ __device__ __forceinline__ float f4_get(const float4& v, int i) {
     return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
 
-template <int H, int TM>
+// SMALL = true : Fin <= 8.  A row = h (H floats); x_t lives in a tiny per-warp slot, W_ih^T in
+//                shared memory; the pipeline streams only W_hh^T (H rows, H/kKC chunks).
+// SMALL = false: A row = [x_t (FinP) | h (H)], the pipeline streams all FinP + H rows
+//                (deeper layers, Fin = H).
+template <int H, int TM, bool SMALL>
 __global__ void __launch_bounds__(kScanThreads, 1)
 reservoir_scan_tiled(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int Fin, int FinP,
                      const float* __restrict__ wpack, const float* __restrict__ bias,
@@ -53,58 +63,82 @@ reservoir_scan_tiled(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, in
     constexpr int NQ = H / 128;
     constexpr int BM = TM * kScanWarps;
     extern __shared__ __align__(16) float smem[];
-    const int Ktot = FinP + H;
-    const int LDA = Ktot + 4;
-    float* arow = smem;                      // [BM][LDA]
-    float* wbuf = smem + (size_t)BM * LDA;   // [kStages][kKC][H]
+    const int KA = SMALL ? H : FinP + H;     // contraction length that goes through the pipeline
+    const int HO = SMALL ? 0 : FinP;         // offset of h inside an A row
+    const int LDA = KA + 4;                  // +4: the look-ahead fragment read past the last quad
+    float* arow = smem;                                        // [BM][LDA]
+    float* wbuf = arow + (size_t)BM * LDA;                     // [kStages][kKC][H] (+ one pad row)
+    float* wih = wbuf + (size_t)(kStages * kKC + 1) * H;       // SMALL: [kSmallFin][H]
+    float* xs = wih + (SMALL ? kSmallFin * H : 0);             // SMALL: [BM][kSmallFin]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0 = blockIdx.x * BM + warp * TM;   // first node of this warp
     float* myrow = arow + (size_t)warp * TM * LDA;
+    float* myx = xs + warp * TM * kSmallFin;
 
-    // ---- initial state and zero padding of the x slot --------------------------------
+    // ---- initial state, zero padding ---------------------------------------------------
 #pragma unroll
     for (int m = 0; m < TM; ++m) {
         const int n = n0 + m;
-        for (int f = lane; f < FinP; f += 32) myrow[m * LDA + f] = 0.f;
+        for (int f = lane; f < HO; f += 32) myrow[m * LDA + f] = 0.f;
+        if (lane < 4) myrow[m * LDA + KA + lane] = 0.f;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (n < N) v = *reinterpret_cast<const float4*>(h_state + (size_t)n * H + q * 128 + lane * 4);
-            *reinterpret_cast<float4*>(myrow + m * LDA + FinP + q * 128 + lane * 4) = v;
+            *reinterpret_cast<float4*>(myrow + m * LDA + HO + q * 128 + lane * 4) = v;
         }
     }
+    if (SMALL) {
+        for (int i = tid; i < kSmallFin * H; i += kScanThreads) wih[i] = (i < FinP * H) ? wpack[i] : 0.f;
+    }
+    for (int i = tid; i < H; i += kScanThreads) wbuf[(size_t)kStages * kKC * H + i] = 0.f;
     float4 bq[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) bq[q] = ldg_f4(bias + q * 128 + lane * 4);
 
-    const int NCH = (Ktot + kKC - 1) / kKC;
+    const float* wsrc = wpack + (SMALL ? (size_t)FinP * H : 0);
+    const int NCH = KA / kKC;
     const long long total = (long long)Tc * NCH;
     auto issue = [&](long long g) {
         if (g < total) {
             const int c = (int)(g % NCH);
-            const int rows = min(kKC, Ktot - c * kKC);
-            const float* src = wpack + (size_t)c * kKC * H;
+            const float* src = wsrc + (size_t)c * kKC * H;
             float* dst = wbuf + (size_t)(g % kStages) * kKC * H;
-            for (int i = tid; i < rows * (H / 4); i += kScanThreads) cp_async16(dst + i * 4, src + i * 4);
+#pragma unroll
+            for (int i = 0; i < kKC * (H / 4) / kScanThreads; ++i)
+                cp_async16(dst + (i * kScanThreads + tid) * 4, src + (i * kScanThreads + tid) * 4);
         }
         cp_async_commit();
     };
     issue(0);
     issue(1);
 
+    // x_t for the small-Fin path: lane l holds element (m = l / 8 + 4*j, f = l % 8) of the slot
+    auto load_x_small = [&](int t, float (&xr)[(TM + 3) / 4]) {
+#pragma unroll
+        for (int j = 0; j < (TM + 3) / 4; ++j) {
+            const int m = (lane >> 3) + 4 * j, f = lane & 7, n = n0 + m;
+            xr[j] = (t < Tc && m < TM && f < Fin && n < N)
+                        ? __ldg(x + (size_t)t * x_ts + (size_t)n * x_ns + f) : 0.f;
+        }
+    };
+    auto store_x_small = [&](const float (&xr)[(TM + 3) / 4]) {
+#pragma unroll
+        for (int j = 0; j < (TM + 3) / 4; ++j) {
+            const int m = (lane >> 3) + 4 * j;
+            if (m < TM) myx[m * kSmallFin + (lane & 7)] = xr[j];
+        }
+    };
+    float xr[(TM + 3) / 4];
+    if (SMALL) {
+        load_x_small(0, xr);
+        store_x_small(xr);
+    }
+    __syncthreads();
+
     long long g = 0;
     for (int t = 0; t < Tc; ++t) {
-        // ---- stage x_t into the warp-private A rows ----------------------------------
-        const float* xt = x + (size_t)t * x_ts;
-#pragma unroll
-        for (int m = 0; m < TM; ++m) {
-            const int n = n0 + m;
-            for (int f = lane; f < Fin; f += 32)
-                myrow[m * LDA + f] = (n < N) ? __ldg(xt + (size_t)n * x_ns + f) : 0.f;
-        }
-        __syncwarp();
-
         float2 acc[TM][NQ][2];
 #pragma unroll
         for (int m = 0; m < TM; ++m)
@@ -113,31 +147,65 @@ reservoir_scan_tiled(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, in
                 acc[m][q][0] = make_float2(bq[q].x, bq[q].y);
                 acc[m][q][1] = make_float2(bq[q].z, bq[q].w);
             }
+        if (SMALL) {
+            // input projection x_t W_ih^T straight into the accumulators
+            for (int f = 0; f < FinP; ++f) {
+                float4 w[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) w[q] = *reinterpret_cast<const float4*>(wih + f * H + q * 128 + lane * 4);
+#pragma unroll
+                for (int m = 0; m < TM; ++m) {
+                    const float xv = myx[m * kSmallFin + f];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) fma4(acc[m][q][0], acc[m][q][1], xv, w[q]);
+                }
+            }
+            __syncwarp();
+            load_x_small(t + 1, xr);      // in flight during the whole contraction below
+        } else {
+            const float* xt = x + (size_t)t * x_ts;
+#pragma unroll
+            for (int m = 0; m < TM; ++m) {
+                const int n = n0 + m;
+                for (int f = lane; f < Fin; f += 32)
+                    myrow[m * LDA + f] = (n < N) ? __ldg(xt + (size_t)n * x_ns + f) : 0.f;
+            }
+            __syncwarp();
+        }
 
         for (int c = 0; c < NCH; ++c, ++g) {
             cp_async_wait<1>();
             __syncthreads();
             issue(g + 2);
             const float* wst = wbuf + (size_t)(g % kStages) * kKC * H + lane * 4;
-            const int rows = min(kKC, Ktot - c * kKC);
             const float* ap = myrow + c * kKC;
-            for (int kq = 0; kq < rows; kq += 4) {
-                float4 a[TM];
+            float4 a_cur[TM], w_cur[NQ];
 #pragma unroll
-                for (int m = 0; m < TM; ++m) a[m] = *reinterpret_cast<const float4*>(ap + m * LDA + kq);
+            for (int m = 0; m < TM; ++m) a_cur[m] = *reinterpret_cast<const float4*>(ap + m * LDA);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) w_cur[q] = *reinterpret_cast<const float4*>(wst + q * 128);
+#pragma unroll 2
+            for (int kq = 0; kq < kKC; kq += 4) {
+                float4 a_nxt[TM];
+#pragma unroll
+                for (int m = 0; m < TM; ++m) a_nxt[m] = *reinterpret_cast<const float4*>(ap + m * LDA + kq + 4);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    float4 w[NQ];
+                    float4 w_nxt[NQ];
 #pragma unroll
                     for (int q = 0; q < NQ; ++q)
-                        w[q] = *reinterpret_cast<const float4*>(wst + (kq + kk) * H + q * 128);
+                        w_nxt[q] = *reinterpret_cast<const float4*>(wst + (kq + kk + 1) * H + q * 128);
 #pragma unroll
                     for (int m = 0; m < TM; ++m) {
-                        const float av = f4_get(a[m], kk);
+                        const float av = f4_get(a_cur[m], kk);
 #pragma unroll
-                        for (int q = 0; q < NQ; ++q) fma4(acc[m][q][0], acc[m][q][1], av, w[q]);
+                        for (int q = 0; q < NQ; ++q) fma4(acc[m][q][0], acc[m][q][1], av, w_cur[q]);
                     }
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) w_cur[q] = w_nxt[q];
                 }
+#pragma unroll
+                for (int m = 0; m < TM; ++m) a_cur[m] = a_nxt[m];
             }
         }
         __syncwarp();   // every lane is done reading this warp's A rows
@@ -160,7 +228,7 @@ reservoir_scan_tiled(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, in
             }
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                float* hp = myrow + m * LDA + FinP + q * 128 + lane * 4;
+                float* hp = myrow + m * LDA + HO + q * 128 + lane * 4;
                 const float4 ho = *reinterpret_cast<const float4*>(hp);
                 float4 z = make_float4(acc[m][q][0].x, acc[m][q][0].y, acc[m][q][1].x, acc[m][q][1].y);
                 if (act == SGP_ACT_SELF_NORM) {
@@ -178,6 +246,7 @@ reservoir_scan_tiled(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, in
                 if (n < N) st_f4(ot + (size_t)n * o_ns + q * 128 + lane * 4, hn);
             }
         }
+        if (SMALL) store_x_small(xr);
         __syncwarp();
     }
     cp_async_wait<0>();
@@ -190,7 +259,7 @@ reservoir_scan_tiled(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, in
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
                 *reinterpret_cast<float4*>(h_state + (size_t)n * H + q * 128 + lane * 4) =
-                    *reinterpret_cast<const float4*>(myrow + m * LDA + FinP + q * 128 + lane * 4);
+                    *reinterpret_cast<const float4*>(myrow + m * LDA + HO + q * 128 + lane * 4);
         }
     }
 }
@@ -252,15 +321,17 @@ __global__ void reservoir_pack_kernel(const float* __restrict__ w_ih, const floa
     }
 }
 
-template <int H, int TM>
+template <int H, int TM, bool SMALL>
 static int launch_tiled(const float* x, int64_t x_ts, int64_t x_ns, int Fin, int FinP,
                         const float* wpack, const float* bias, float alpha, float oma, int act,
                         float* h_state, float* out, int64_t o_ts, int64_t o_ns, int Tc, int N,
                         cudaStream_t st) {
     constexpr int BM = TM * kScanWarps;
-    const size_t smem = ((size_t)BM * (FinP + H + 4) + (size_t)kStages * kKC * H) * sizeof(float);
-    if (smem > 227 * 1024) return 1;   // caller falls back to a smaller TM
-    auto kern = reservoir_scan_tiled<H, TM>;
+    const int KA = SMALL ? H : FinP + H;
+    const size_t smem = ((size_t)BM * (KA + 4) + (size_t)(kStages * kKC + 1) * H +
+                         (SMALL ? (size_t)kSmallFin * H + (size_t)BM * kSmallFin : 0)) * sizeof(float);
+    if (smem > 227 * 1024) return 1;   // caller falls back to a narrower node tile
+    auto kern = reservoir_scan_tiled<H, TM, SMALL>;
     SGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (N + BM - 1) / BM;
     kern<<<grid, kScanThreads, smem, st>>>(x, x_ts, x_ns, Fin, FinP, wpack, bias, alpha, oma, act,
@@ -269,15 +340,36 @@ static int launch_tiled(const float* x, int64_t x_ts, int64_t x_ns, int Fin, int
     return SGP_OK;
 }
 
+template <int H, bool SMALL>
+static int launch_tiled_h(const float* x, int64_t x_ts, int64_t x_ns, int Fin, int FinP,
+                          const float* wpack, const float* bias, float alpha, float oma, int act,
+                          float* h_state, float* out, int64_t o_ts, int64_t o_ns, int Tc, int N,
+                          cudaStream_t st) {
+    // enough CTAs to fill the machine first, then the widest node tile that fits shared memory
+    int rc = 1;
+#define SGP_TRY(TM_)                                                                              \
+    if (rc == 1) rc = launch_tiled<H, TM_, SMALL>(x, x_ts, x_ns, Fin, FinP, wpack, bias, alpha, oma, \
+                                                  act, h_state, out, o_ts, o_ns, Tc, N, st)
+    if (N >= 64 * kNumSMs) SGP_TRY(8);
+    if (N >= 32 * kNumSMs) SGP_TRY(4);
+    SGP_TRY(2);
+#undef SGP_TRY
+    return rc;
+}
+
 }  // namespace sgp
 
 using namespace sgp;
+
+extern "C" int sgp_reservoir_pack_rows(int Fin, int H) {
+    return (Fin >= 1 && H >= 1) ? fin_padded(Fin) + H : 0;
+}
 
 extern "C" int sgp_reservoir_pack(const float* w_ih, const float* w_hh, int Fin, int H, float* wpack,
                                   void* stream) {
     SGP_REQUIRE(w_ih && w_hh && wpack, SGP_EINVAL, "sgp_reservoir_pack: null pointer");
     SGP_REQUIRE(Fin >= 1 && H >= 1, SGP_EINVAL, "sgp_reservoir_pack: Fin=%d H=%d", Fin, H);
-    const int FinP = (Fin + 3) & ~3;
+    const int FinP = fin_padded(Fin);
     const int64_t total = (int64_t)(FinP + H) * H;
     const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     reservoir_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_ih, w_hh, Fin, FinP, H, wpack);
@@ -297,21 +389,16 @@ extern "C" int sgp_reservoir_scan(const float* x, int64_t x_t_stride, int64_t x_
                 "sgp_reservoir_scan: unknown activation code %d", act);
     if (N == 0 || Tc == 0) return SGP_OK;
     cudaStream_t st = as_stream(stream);
-    const int FinP = (Fin + 3) & ~3;
+    const int FinP = fin_padded(Fin);
     const bool vec_ok = aligned16(out) && aligned16(h_state) && aligned16(wpack) && aligned16(bias) &&
                         out_t_stride % 4 == 0 && out_n_stride % 4 == 0;
     if ((H == 128 || H == 256) && vec_ok) {
-        int rc = 1;
-        // enough CTAs to fill the machine first, then the widest tile that fits shared memory
-        if (H == 256) {
-            if (N >= 64 * kNumSMs) rc = launch_tiled<256, 8>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
-            if (rc == 1 && N >= 32 * kNumSMs) rc = launch_tiled<256, 4>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
-            if (rc == 1) rc = launch_tiled<256, 2>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
-        } else {
-            if (N >= 64 * kNumSMs) rc = launch_tiled<128, 8>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
-            if (rc == 1 && N >= 32 * kNumSMs) rc = launch_tiled<128, 4>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
-            if (rc == 1) rc = launch_tiled<128, 2>(x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st);
-        }
+        int rc;
+#define SGP_ARGS x, x_t_stride, x_n_stride, Fin, FinP, wpack, bias, alpha, one_minus_alpha, act, h_state, \
+                 out, out_t_stride, out_n_stride, Tc, N, st
+        if (H == 256) rc = Fin <= kSmallFin ? launch_tiled_h<256, true>(SGP_ARGS) : launch_tiled_h<256, false>(SGP_ARGS);
+        else rc = Fin <= kSmallFin ? launch_tiled_h<128, true>(SGP_ARGS) : launch_tiled_h<128, false>(SGP_ARGS);
+#undef SGP_ARGS
         if (rc != 1) return rc;
     }
     const size_t smem = (size_t)kGenWarps * (FinP + 2 * (size_t)H) * sizeof(float);

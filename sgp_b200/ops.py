@@ -80,8 +80,8 @@ def csr_build(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num
 def reservoir_pack(w_ih: torch.Tensor, w_hh: torch.Tensor) -> torch.Tensor:
     _require_cuda(w_ih, w_hh)
     H, Fin = w_ih.shape
-    FinP = (Fin + 3) // 4 * 4
-    out = torch.empty(FinP + H, H, dtype=torch.float32, device=w_ih.device)
+    rows = int(load().sgp_reservoir_pack_rows(Fin, H))
+    out = torch.empty(rows, H, dtype=torch.float32, device=w_ih.device)
     check(load().sgp_reservoir_pack(_p(w_ih.contiguous()), _p(w_hh.contiguous()), Fin, H, _p(out),
                                     _stream(w_ih.device)), "sgp_reservoir_pack")
     return out
