@@ -280,7 +280,7 @@ def run_own(args, cfg):
     scan_n, scan_ms = summ.get("scan", (0, 0.0))
     scan_flops = N * T * (2 * H * (Fin + H) + 6 * H) * args.steps
     fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    roofline = dict(bound="hbm", kernel="spmm_rbu_kernel<16>" if fwd.rbu is not None else "spmm_csr_vec",
+    roofline = dict(bound="hbm", kernel=("spmm_rbu_v3<%d>" % fwd.rbu.R) if fwd.rbu is not None else "spmm_csr_vec",
                     achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
                     peak_source=peaks["source"], traffic=None,
                     algorithmic_bytes_per_launch=bytes_per_launch, timesteps_per_launch=step_T,

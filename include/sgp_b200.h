@@ -113,6 +113,13 @@ int sgp_spmm(const int32_t* rowptr, const int32_t* col, const float* val, const 
              const float* src, int64_t src_t_stride, int64_t src_n_stride,
              float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
              int n_rows, int F, int Tc, void* stream);
+/* Row-sharded variant: column ids < n_split address `src` (the rank's own rows), ids >= n_split
+ * address row (id - n_split) of `src2` (halo rows received from the other ranks). */
+int sgp_spmm_halo(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* row_order,
+                  const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                  const float* src2, int64_t src2_t_stride, int64_t src2_n_stride, int n_split,
+                  float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+                  int n_rows, int F, int Tc, void* stream);
 int sgp_khop_spmm(const int32_t* rowptr, const int32_t* col, const float* val,
                   const int32_t* row_order,
                   float* buf, int64_t t_stride, int64_t n_stride,
@@ -131,6 +138,13 @@ int sgp_spmm_rbu(const int32_t* grp_ptr, const int32_t* grp_rows, const int32_t*
                  const float* src, int64_t src_t_stride, int64_t src_n_stride,
                  float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
                  int F, int Tc, void* stream);
+
+int sgp_spmm_rbu_halo(const int32_t* grp_ptr, const int32_t* grp_rows, const int32_t* ucol,
+                      const float* uval, int R, int n_groups,
+                      const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                      const float* src2, int64_t src2_t_stride, int64_t src2_n_stride, int n_split,
+                      float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+                      int F, int Tc, void* stream);
 
 /* HOST function (pointers are host memory, no stream): choose the R-row groups of the RBU format
  * from a CSR operator by a breadth-first, heaviest-neighbour-first greedy (group_rows.cu).
