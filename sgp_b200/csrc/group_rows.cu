@@ -37,6 +37,7 @@ extern "C" int sgp_group_rows(const int32_t* rowptr, const int32_t* col, const f
             const int32_t i = order[head++];
             for (int32_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
                 const int32_t j = col[e];
+                if (j >= N) continue;     // rectangular operator (halo columns): not a row
                 if (!seen[j]) { seen[j] = 1; order.push_back(j); }
             }
         }
@@ -52,7 +53,7 @@ extern "C" int sgp_group_rows(const int32_t* rowptr, const int32_t* col, const f
         cand.clear();
         for (int32_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
             const int32_t j = col[e];
-            if (j != i && !taken[j]) cand.emplace_back(-val[e], j);
+            if (j != i && j < N && !taken[j]) cand.emplace_back(-val[e], j);
         }
         std::sort(cand.begin(), cand.end());
         if ((int32_t)cand.size() < R - 1) { late.push_back(i); continue; }

@@ -104,16 +104,22 @@ def reservoir_scan(x: torch.Tensor, wpack: torch.Tensor, bias: torch.Tensor, alp
 
 
 def spmm(csr: Csr, src: torch.Tensor, dst: torch.Tensor, row_order: Optional[torch.Tensor] = None,
-         n_rows: Optional[int] = None) -> None:
-    _require_cuda(src, dst, csr.rowptr)
+         n_rows: Optional[int] = None, halo: Optional[torch.Tensor] = None, n_split: int = 0) -> None:
+    _require_cuda(src, dst, csr.rowptr, halo)
     _check_view3(src, "src")
     _check_view3(dst, "dst")
     Tc, _, F = src.shape
     rows = int(csr.rowptr.numel() - 1) if n_rows is None else n_rows
     assert dst.shape[0] == Tc and dst.shape[2] == F and dst.shape[1] >= rows
-    check(load().sgp_spmm(_p(csr.rowptr), _p(csr.col), _p(csr.val), _p(row_order),
-                          _p(src), src.stride(0), src.stride(1), _p(dst), dst.stride(0), dst.stride(1),
-                          rows, F, Tc, _stream(src.device)), "sgp_spmm")
+    if halo is None:
+        h_ptr, h_ts, h_ns = None, 0, 0
+    else:
+        _check_view3(halo, "halo")
+        h_ptr, h_ts, h_ns = _p(halo), halo.stride(0), halo.stride(1)
+    check(load().sgp_spmm_halo(_p(csr.rowptr), _p(csr.col), _p(csr.val), _p(row_order),
+                               _p(src), src.stride(0), src.stride(1), h_ptr, h_ts, h_ns, n_split,
+                               _p(dst), dst.stride(0), dst.stride(1), rows, F, Tc,
+                               _stream(src.device)), "sgp_spmm")
 
 
 def khop_spmm(csr: Csr, buf: torch.Tensor, block_in: int, block_out0: int, hops: int, F: int,
@@ -152,13 +158,16 @@ def group_rows_host(rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, N: int
     return out[: n_groups * R].reshape(n_groups, R)
 
 
-def rbu_build(csr: Csr, R: int) -> Rbu:
-    """Group rows on the host (needs the CSR there once), then assemble the union slabs on the
-    device with sort/unique/scatter (one-off, O(nnz))."""
+def rbu_build(csr: Csr, R: int, grp_rows_h: Optional[np.ndarray] = None,
+              n_cols: Optional[int] = None) -> Rbu:
+    """Group rows on the host (needs the CSR there once) unless `grp_rows_h` [n_groups, R] is
+    given, then assemble the union slabs on the device with sort/unique/scatter (one-off,
+    O(nnz)).  `n_cols` > num rows for a rectangular (row-sharded, local + halo columns) operator."""
     dev = csr.rowptr.device
     N = csr.num_nodes
-    grp_rows_h = group_rows_host(csr.rowptr.cpu().numpy(), csr.col.cpu().numpy(),
-                                 csr.val.cpu().numpy(), N, R)
+    if grp_rows_h is None:
+        grp_rows_h = group_rows_host(csr.rowptr.cpu().numpy(), csr.col.cpu().numpy(),
+                                     csr.val.cpu().numpy(), N, R)
     n_groups = grp_rows_h.shape[0]
     grp_rows = torch.from_numpy(grp_rows_h).to(dev)
     flat = grp_rows.reshape(-1).to(torch.int64)
@@ -169,11 +178,12 @@ def rbu_build(csr: Csr, R: int) -> Rbu:
     row_of_e = torch.repeat_interleave(torch.arange(N, device=dev), counts)
     gs = slot_of[row_of_e]
     g_e, s_e = gs // R, gs % R
-    key = g_e * N + csr.col.to(torch.int64)
+    NC = int(n_cols) if n_cols is not None else N
+    key = g_e * NC + csr.col.to(torch.int64)
     ukey, inv = torch.unique(key, return_inverse=True)
     total_u = int(ukey.numel())
-    ucol = (ukey % N).to(torch.int32)
-    ugrp = ukey // N
+    ucol = (ukey % NC).to(torch.int32)
+    ugrp = ukey // NC
     grp_ptr = torch.zeros(n_groups + 1, dtype=torch.int64, device=dev)
     grp_ptr[1:] = torch.cumsum(torch.bincount(ugrp, minlength=n_groups), 0)
     uval = torch.zeros(max(total_u, 1), R, dtype=torch.float32, device=dev)
@@ -182,14 +192,22 @@ def rbu_build(csr: Csr, R: int) -> Rbu:
     return Rbu(grp_ptr.to(torch.int32), grp_rows.contiguous(), ucol, uval, R, n_groups, fill)
 
 
-def spmm_rbu(rbu: Rbu, src: torch.Tensor, dst: torch.Tensor) -> None:
-    _require_cuda(src, dst)
+def spmm_rbu(rbu: Rbu, src: torch.Tensor, dst: torch.Tensor, halo: Optional[torch.Tensor] = None,
+             n_split: int = 0) -> None:
+    """dst = S @ [src ; halo]: column ids < n_split index `src`, the rest index `halo` rows."""
+    _require_cuda(src, dst, halo)
     _check_view3(src, "src")
     _check_view3(dst, "dst")
     Tc, _, F = src.shape
-    check(load().sgp_spmm_rbu(_p(rbu.grp_ptr), _p(rbu.grp_rows), _p(rbu.ucol), _p(rbu.uval), rbu.R,
-                              rbu.n_groups, _p(src), src.stride(0), src.stride(1), _p(dst),
-                              dst.stride(0), dst.stride(1), F, Tc, _stream(src.device)), "sgp_spmm_rbu")
+    if halo is None:
+        h_ptr, h_ts, h_ns = None, 0, 0
+    else:
+        _check_view3(halo, "halo")
+        h_ptr, h_ts, h_ns = _p(halo), halo.stride(0), halo.stride(1)
+    check(load().sgp_spmm_rbu_halo(_p(rbu.grp_ptr), _p(rbu.grp_rows), _p(rbu.ucol), _p(rbu.uval), rbu.R,
+                                   rbu.n_groups, _p(src), src.stride(0), src.stride(1), h_ptr, h_ts, h_ns,
+                                   n_split, _p(dst), dst.stride(0), dst.stride(1), F, Tc,
+                                   _stream(src.device)), "sgp_spmm_rbu")
 
 
 def node_sum(src: torch.Tensor, sums: torch.Tensor) -> None:

@@ -31,10 +31,11 @@ _RBU_MIN_FILL = {16: 0.30, 8: 0.40, 4: 0.55}
 class ShiftOperator:
     """Normalised graph-shift operator resident on one GPU (what ``preprocess_adj`` returns)."""
 
-    def __init__(self, csr: ops.Csr, rbu: Optional[ops.Rbu] = None):
+    def __init__(self, csr: ops.Csr, rbu: Optional[ops.Rbu] = None, n_split: int = 0):
         self.csr = csr
         self.rbu = rbu
         self.num_nodes = csr.num_nodes
+        self.n_split = n_split      # row-sharded: column ids >= n_split address the halo buffer
 
     @property
     def device(self):
@@ -65,14 +66,15 @@ class ShiftOperator:
                 self.rbu = cand
                 return
 
-    def apply(self, src: Tensor, dst: Tensor) -> None:
-        """dst[t] = S @ src[t] for [T, N, F] device views (dst must not alias src)."""
+    def apply(self, src: Tensor, dst: Tensor, halo: Optional[Tensor] = None) -> None:
+        """dst[t] = S @ src[t] for [T, N, F] device views (dst must not alias src); with `halo`
+        [T, n_halo, F] the operator's column ids >= n_split read halo rows."""
         F = src.size(-1)
         if (self.rbu is not None and F % 128 == 0 and src.data_ptr() % 16 == 0 and
                 dst.data_ptr() % 16 == 0 and all(s % 4 == 0 for s in (*src.stride()[:2], *dst.stride()[:2]))):
-            ops.spmm_rbu(self.rbu, src, dst)
+            ops.spmm_rbu(self.rbu, src, dst, halo, self.n_split)
         else:
-            ops.spmm(self.csr, src, dst)
+            ops.spmm(self.csr, src, dst, halo=halo, n_split=self.n_split)
 
     def __matmul__(self, x: Tensor) -> Tensor:
         """``adj @ x`` for x [N, F] or [..., N, F]; result on x's device."""

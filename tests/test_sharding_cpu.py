@@ -1,0 +1,104 @@
+"""Host logic of the row-sharded path on CPU: partition / halo plan (numpy) and the all-to-all-v
+exchange pattern with world_size 2 and 3 over gloo.  The device kernels are not involved; the
+SpMM check uses scipy on the plan's local CSR."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import sgp_oracle as O
+from sgp_b200.sharded import build_plans
+from sgp_b200.synthetic import sensor_knn
+from tests.helpers import random_graph
+
+
+def _global_csr(n, kind):
+    if kind == "knn":
+        ei, ew = sensor_knn(n, 12, seed=4)
+    else:
+        ei, ew = random_graph(n, 9 * n, seed=4)
+    return O.build_operator(ei, ew, n, set_diag=False)
+
+
+@pytest.mark.parametrize("kind", ["knn", "random"])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_plans_cover_rows_and_reproduce_spmm(kind, world):
+    n, F = 803, 5
+    rowptr, col, val = _global_csr(n, kind)
+    plans = build_plans(rowptr, col, val, n, world, R=4)
+    assert sorted(np.concatenate([p.own for p in plans]).tolist()) == list(range(n))
+    X = np.random.default_rng(0).standard_normal((n, F)).astype(np.float32)
+    S = sp.csr_matrix((val, col, rowptr), shape=(n, n))
+    want = S @ X
+    for p in plans:
+        assert not np.intersect1d(p.own, p.halo).size
+        assert p.recv_counts.sum() == p.halo.size and p.send_counts.sum() == p.send_index.size
+        assert p.recv_counts[p.rank] == 0 and p.send_counts[p.rank] == 0
+        local = sp.csr_matrix((p.val, p.col, p.rowptr), shape=(p.n_own, p.n_own + p.n_halo))
+        src = np.concatenate([X[p.own], X[p.halo]])
+        np.testing.assert_allclose(local @ src, want[p.own], rtol=1e-5, atol=1e-6)
+        flat = p.grp_rows.reshape(-1)
+        assert sorted(flat[flat >= 0].tolist()) == list(range(p.n_own))
+    # what rank q sends to p is exactly p's halo segment for q, in the same order
+    for p in plans:
+        off = np.concatenate([[0], np.cumsum(p.recv_counts)])
+        for q in plans:
+            soff = np.concatenate([[0], np.cumsum(q.send_counts)])
+            sent = q.own[q.send_index[soff[p.rank]:soff[p.rank + 1]]]
+            np.testing.assert_array_equal(sent, p.halo[off[q.rank]:off[q.rank + 1]])
+    if kind == "knn" and world == 2:
+        assert sum(p.n_halo for p in plans) < 0.5 * n       # locality-aware: small halo
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, F, Tc, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rowptr, col, val = _global_csr(n, "knn")
+        plan = build_plans(rowptr, col, val, n, world, R=4, ranks=[rank])[0]
+        X = torch.from_numpy(np.random.default_rng(1).standard_normal((Tc, n, F)).astype(np.float32))
+        own = torch.from_numpy(plan.own)
+        block = X[:, own]                                          # [Tc, n_own, F]
+        # node-major packing, exactly like RowShardedEncoder._exchange
+        send = block[:, torch.from_numpy(plan.send_index).long()].permute(1, 0, 2).contiguous()
+        halo = torch.empty(plan.n_halo, Tc, F)
+        per = Tc * F
+        dist.all_to_all_single(halo.view(-1), send.view(-1), [int(c) * per for c in plan.recv_counts],
+                               [int(c) * per for c in plan.send_counts])
+        ok = torch.equal(halo.permute(1, 0, 2), X[:, torch.from_numpy(plan.halo)])
+        S = sp.csr_matrix((val, col, rowptr), shape=(n, n))
+        local = sp.csr_matrix((plan.val, plan.col, plan.rowptr), shape=(plan.n_own, plan.n_own + plan.n_halo))
+        for t in range(Tc):
+            src = np.concatenate([block[t].numpy(), halo[:, t].numpy()])
+            ok = ok and np.allclose(local @ src, (S @ X[t].numpy())[plan.own], rtol=1e-5, atol=1e-6)
+        flag = torch.tensor([1.0 if ok else 0.0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret.put(float(flag))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 400, 6, 3, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=10) == 1.0
