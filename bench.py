@@ -263,6 +263,7 @@ def run_own(args, cfg):
     torch.cuda.synchronize()
     launches = _lib.launch_count() - l0
     clocks = sampler.stop()
+    fwd.check()
     ms_step = e0.elapsed_time(e1) / args.steps
     value = N * T / (ms_step * 1e-3)
 
@@ -280,7 +281,8 @@ def run_own(args, cfg):
     scan_n, scan_ms = summ.get("scan", (0, 0.0))
     scan_flops = N * T * (2 * H * (Fin + H) + 6 * H) * args.steps
     fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    roofline = dict(bound="hbm", kernel=("spmm_rbu_v3<%d>" % fwd.rbu.R) if fwd.rbu is not None else "spmm_csr_vec",
+    roofline = dict(bound="hbm", kernel=("spmm_rbu_tc_kernel (tcgen05, 3xTF32)" if fwd.tc is not None else
+                            ("spmm_rbu_v3<%d>" % fwd.rbu.R) if fwd.rbu is not None else "spmm_csr_vec"),
                     achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
                     peak_source=peaks["source"], traffic=None,
                     algorithmic_bytes_per_launch=bytes_per_launch, timesteps_per_launch=step_T,
@@ -314,7 +316,7 @@ def run_own(args, cfg):
         t_e2e.append(time.perf_counter() - t0)
     e2e_s = sum(t_e2e) / len(t_e2e)
     h2d = x.nbytes + ei.nbytes + ew.nbytes
-    d2h = 8 + (4 * (N + 1) + 8 * nnz if fwd.rbu is not None else 0)
+    d2h = 8 + (4 * (N + 1) + 8 * nnz if (fwd.rbu is not None or fwd.tc is not None) else 0)
     e2e = dict(value=N * T / e2e_s, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                ms_per_step=e2e_s * 1e3, checksum=chk,
                note="SGPEncoder.encode_stream on pinned host x + host edge list: H2D of inputs, operator "
@@ -341,8 +343,11 @@ def run_own(args, cfg):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype="f32", data="synthetic",
-                config=config_dict(cfg, 1, extra=dict(chunk_steps=step_T, rbu_R=fwd.rbu.R if fwd.rbu else 0,
-                                                      rbu_fill=round(fwd.rbu.fill, 3) if fwd.rbu else None)),
+                config=config_dict(cfg, 1, extra=dict(
+                    chunk_steps=step_T,
+                    operator_format=("tcgen05 64-row groups" if fwd.tc is not None else
+                                     "rbu%d" % fwd.rbu.R if fwd.rbu is not None else "csr"),
+                    group_fill=round((fwd.tc or fwd.rbu).fill, 3) if (fwd.tc or fwd.rbu) else None)),
                 roofline=roofline, reservoir=reservoir, cpu_baseline=cpu, e2e=e2e, clocks=clocks,
                 gpu_launches=int(launches), checksum=float(acc))
     print(json.dumps(line))

@@ -146,6 +146,19 @@ int sgp_spmm_rbu_halo(const int32_t* grp_ptr, const int32_t* grp_rows, const int
                       float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
                       int F, int Tc, void* stream);
 
+/* Tensor-core hop (tcgen05, 3xTF32, fp32-accurate): rows grouped 64 at a time, union columns padded
+ * to chunks of 32.  chunk_ptr [n_groups+1] (in chunks), grp_rows [n_groups, 64] (-1 = padding),
+ * cols [total_chunks*32] source row ids, bimg [total_chunks][2][64*32] the chunk's operator values
+ * as tf32 hi / lo images in the K-major SWIZZLE_128B shared-memory layout (built by
+ * sgp_b200/ops.py::tc_build).  F in {128, 256, 512, 1024}.  *err_flag (device int) is set to 1 if
+ * an internal barrier times out.  src2 / n_split as in sgp_spmm_halo. */
+int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int32_t* cols,
+                    const float* bimg, int n_groups,
+                    const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                    const float* src2, int64_t src2_t_stride, int64_t src2_n_stride, int n_split,
+                    float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+                    int F, int Tc, int* err_flag, void* stream);
+
 /* HOST function (pointers are host memory, no stream): choose the R-row groups of the RBU format
  * from a CSR operator by a breadth-first, heaviest-neighbour-first greedy (group_rows.cu).
  * grp_rows must hold ceil(N/R)*R entries; unused slots of the last group are set to -1. */

@@ -40,6 +40,9 @@ SIGNATURES = {
     "sgp_spmm_rbu_halo": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64,
                                   c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64,
                                   c_int, c_int, c_void_p]),
+    "sgp_spmm_rbu_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64,
+                                c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int, c_int,
+                                c_void_p, c_void_p]),
     "sgp_group_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "sgp_node_sum": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sgp_node_mean_broadcast": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,

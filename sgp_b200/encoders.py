@@ -124,6 +124,9 @@ class SGPSpatialEncoder(nn.Module):
             self.encode_chunk(buf, F, fwd, bwd)
             if not x.is_cuda:
                 out[t0:t1] = buf.to(x.device)
+        for op in (fwd, bwd):
+            if op is not None:
+                op.check()
         return out[0] if squeeze else out
 
     @staticmethod
@@ -178,6 +181,9 @@ class SGPEncoder(nn.Module):
             res.scan_chunk(plan, xc, state, buf)
             spat.encode_chunk(buf, F, fwd, bwd, sums)
             sink(t0, t1, buf)
+        for op in (fwd, bwd):
+            if op is not None:
+                op.check()
 
     def forward(self, x, edge_index, edge_weight):
         """x [T, N, Fin] on CPU or GPU -> [T, N, D] on the same device."""

@@ -210,6 +210,96 @@ def spmm_rbu(rbu: Rbu, src: torch.Tensor, dst: torch.Tensor, halo: Optional[torc
                                    _stream(src.device)), "sgp_spmm_rbu")
 
 
+@dataclass
+class TcOp:
+    """Tensor-core operator format (see sgp_spmm_rbu_tc in include/sgp_b200.h)."""
+    chunk_ptr: torch.Tensor      # [n_groups+1] int32
+    grp_rows: torch.Tensor       # [n_groups, 64] int32
+    cols: torch.Tensor           # [total_chunks*32] int32
+    bimg: torch.Tensor           # [total_chunks, 2, 2048] float32
+    n_groups: int
+    fill: float
+    err: torch.Tensor            # device int32 flag
+
+
+TC_R, TC_KC = 64, 32
+
+
+def tc_build(csr: Csr, grp_rows_h: Optional[np.ndarray] = None, n_cols: Optional[int] = None) -> TcOp:
+    """Build the tcgen05 operator format from a CSR: 64-row locality groups, per group the sorted
+    union of columns padded to chunks of 32, and per chunk the [64 x 32] slab of values split into
+    tf32 hi / lo images laid out exactly as the kernel's K-major SWIZZLE_128B shared-memory tile."""
+    dev = csr.rowptr.device
+    N, R, KC = csr.num_nodes, TC_R, TC_KC
+    if grp_rows_h is None:
+        grp_rows_h = group_rows_host(csr.rowptr.cpu().numpy(), csr.col.cpu().numpy(),
+                                     csr.val.cpu().numpy(), N, R)
+    n_groups = grp_rows_h.shape[0]
+    grp_rows = torch.from_numpy(np.ascontiguousarray(grp_rows_h)).to(dev)
+    flat = grp_rows.reshape(-1).to(torch.int64)
+    valid = flat >= 0
+    slot_of = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+    slot_of[flat[valid]] = torch.arange(flat.numel(), device=dev)[valid]
+    counts = (csr.rowptr[1:] - csr.rowptr[:-1]).to(torch.int64)
+    row_of_e = torch.repeat_interleave(torch.arange(N, device=dev), counts)
+    gs = slot_of[row_of_e]
+    g_e, s_e = gs // R, gs % R
+    NC = int(n_cols) if n_cols is not None else N
+    ukey, inv = torch.unique(g_e * NC + csr.col.to(torch.int64), return_inverse=True)
+    ugrp, ucol = ukey // NC, (ukey % NC).to(torch.int32)
+    cnt = torch.bincount(ugrp, minlength=n_groups)
+    chunks = (cnt + KC - 1) // KC
+    chunk_ptr = torch.zeros(n_groups + 1, dtype=torch.int64, device=dev)
+    chunk_ptr[1:] = torch.cumsum(chunks, 0)
+    total_chunks = int(chunk_ptr[-1])
+    first_u = torch.zeros(n_groups + 1, dtype=torch.int64, device=dev)
+    first_u[1:] = torch.cumsum(cnt, 0)
+    # position of every union entry inside the padded column array
+    pos_u = chunk_ptr[ugrp] * KC + (torch.arange(ukey.numel(), device=dev) - first_u[ugrp])
+    cols = torch.zeros(max(total_chunks * KC, 1), dtype=torch.int32, device=dev)
+    if ukey.numel():
+        # padding slots repeat the group's first column (their slab values are zero)
+        fill_col = ucol[first_u[:-1].clamp(max=ukey.numel() - 1)]
+        chunk_grp = torch.repeat_interleave(torch.arange(n_groups, device=dev), chunks)
+        cols[: total_chunks * KC] = fill_col[chunk_grp].repeat_interleave(KC)
+        cols[pos_u] = ucol
+    # slab images: entry (slot s, padded position p) -> chunk p // 32, k = p % 32
+    p_e = pos_u[inv]
+    chunk_e, k_e = p_e // KC, p_e % KC
+    off = (s_e >> 3) * 256 + (s_e & 7) * 32 + (((k_e >> 2) ^ (s_e & 7)) << 2) + (k_e & 3)   # in floats
+    img = torch.zeros(max(total_chunks, 1) * R * KC, dtype=torch.float32, device=dev)
+    img.index_put_((chunk_e * (R * KC) + off,), csr.val, accumulate=True)
+    hi = (img.view(torch.int32) & -8192).view(torch.float32)          # clear the low 13 mantissa bits
+    lo = img - hi
+    bimg = torch.stack([hi.view(-1, R * KC), lo.view(-1, R * KC)], dim=1).contiguous()
+    fill = csr.nnz / max(int(cnt.sum()) * R, 1)
+    return TcOp(chunk_ptr.to(torch.int32), grp_rows.contiguous(), cols, bimg, n_groups, fill,
+                torch.zeros(1, dtype=torch.int32, device=dev))
+
+
+def spmm_tc(tc: TcOp, src: torch.Tensor, dst: torch.Tensor, halo: Optional[torch.Tensor] = None,
+            n_split: int = 0) -> None:
+    _require_cuda(src, dst, halo)
+    _check_view3(src, "src")
+    _check_view3(dst, "dst")
+    Tc, _, F = src.shape
+    if halo is None:
+        h_ptr, h_ts, h_ns = None, 0, 0
+    else:
+        _check_view3(halo, "halo")
+        h_ptr, h_ts, h_ns = _p(halo), halo.stride(0), halo.stride(1)
+    check(load().sgp_spmm_rbu_tc(_p(tc.chunk_ptr), _p(tc.grp_rows), _p(tc.cols), _p(tc.bimg), tc.n_groups,
+                                 _p(src), src.stride(0), src.stride(1), h_ptr, h_ts, h_ns, n_split,
+                                 _p(dst), dst.stride(0), dst.stride(1), F, Tc, _p(tc.err),
+                                 _stream(src.device)), "sgp_spmm_rbu_tc")
+
+
+def tc_check(tc: TcOp) -> None:
+    """Raise if a tensor-core launch reported an internal barrier timeout (synchronises)."""
+    if int(tc.err.item()) != 0:
+        raise _lib.SgpError("sgp_spmm_rbu_tc: internal barrier timed out (results invalid)")
+
+
 def node_sum(src: torch.Tensor, sums: torch.Tensor) -> None:
     _check_view3(src, "src")
     Tc, N, F = src.shape

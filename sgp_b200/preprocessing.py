@@ -26,14 +26,18 @@ from .reservoir import Reservoir, _cuda_device_for
 # rows are grouped for the RBU kernel when the graph is big enough for gather traffic to matter
 _RBU_MIN_NNZ = int(os.environ.get("SGP_B200_RBU_MIN_NNZ", 200_000))
 _RBU_MIN_FILL = {16: 0.30, 8: 0.40, 4: 0.55}
+_TC_MIN_FILL = 0.10      # 64-row groups: the tensor-core hop wins as long as the slabs are >= 10 % dense
 
 
 class ShiftOperator:
     """Normalised graph-shift operator resident on one GPU (what ``preprocess_adj`` returns)."""
 
-    def __init__(self, csr: ops.Csr, rbu: Optional[ops.Rbu] = None, n_split: int = 0):
+    def __init__(self, csr: ops.Csr, rbu: Optional[ops.Rbu] = None, n_split: int = 0,
+                 tc: Optional[ops.TcOp] = None, n_cols: Optional[int] = None):
         self.csr = csr
         self.rbu = rbu
+        self.tc = tc
+        self.n_cols = n_cols        # > num rows for a row-sharded (local + halo columns) operator
         self.num_nodes = csr.num_nodes
         self.n_split = n_split      # row-sharded: column ids >= n_split address the halo buffer
 
@@ -52,16 +56,23 @@ class ShiftOperator:
         return self.csr.rowptr, self.csr.col, self.csr.val
 
     def maybe_build_rbu(self, F: int, mode: str = "auto") -> None:
-        """Attach the RBU format when it pays: F % 128 == 0 and the greedy groups are dense enough."""
-        if self.rbu is not None or mode == "off" or F % 128 != 0:
+        """Attach a grouped format when it pays (F % 128 == 0 and the greedy groups are dense
+        enough): the tensor-core format (64-row groups) first, else the CUDA-core RBU format.
+        mode: "auto" | "off" | "tc" | "rbu" | "force4/8/16"."""
+        if self.rbu is not None or self.tc is not None or mode == "off" or F % 128 != 0:
             return
         if mode == "auto" and self.csr.nnz < _RBU_MIN_NNZ:
             return
         if mode.startswith("force"):
-            self.rbu = ops.rbu_build(self.csr, int(mode[len("force"):]))
+            self.rbu = ops.rbu_build(self.csr, int(mode[len("force"):]), n_cols=self.n_cols)
             return
+        if mode in ("auto", "tc") and (F // 128) in (1, 2, 4, 8):
+            cand = ops.tc_build(self.csr, n_cols=self.n_cols)
+            if cand.fill >= _TC_MIN_FILL or mode == "tc":
+                self.tc = cand
+                return
         for R in (16, 8, 4):
-            cand = ops.rbu_build(self.csr, R)
+            cand = ops.rbu_build(self.csr, R, n_cols=self.n_cols)
             if cand.fill >= _RBU_MIN_FILL[R]:
                 self.rbu = cand
                 return
@@ -70,11 +81,19 @@ class ShiftOperator:
         """dst[t] = S @ src[t] for [T, N, F] device views (dst must not alias src); with `halo`
         [T, n_halo, F] the operator's column ids >= n_split read halo rows."""
         F = src.size(-1)
-        if (self.rbu is not None and F % 128 == 0 and src.data_ptr() % 16 == 0 and
-                dst.data_ptr() % 16 == 0 and all(s % 4 == 0 for s in (*src.stride()[:2], *dst.stride()[:2]))):
+        aligned = (F % 128 == 0 and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0 and
+                   all(s % 4 == 0 for s in (*src.stride()[:2], *dst.stride()[:2])))
+        if self.tc is not None and aligned and (F // 128) in (1, 2, 4, 8):
+            ops.spmm_tc(self.tc, src, dst, halo, self.n_split)
+        elif self.rbu is not None and aligned:
             ops.spmm_rbu(self.rbu, src, dst, halo, self.n_split)
         else:
             ops.spmm(self.csr, src, dst, halo=halo, n_split=self.n_split)
+
+    def check(self) -> None:
+        """Raise if a tensor-core launch of this operator reported a barrier timeout (syncs)."""
+        if self.tc is not None:
+            ops.tc_check(self.tc)
 
     def __matmul__(self, x: Tensor) -> Tensor:
         """``adj @ x`` for x [N, F] or [..., N, F]; result on x's device."""
@@ -220,6 +239,9 @@ def sgp_spatial_embedding(x, num_nodes, edge_index, edge_weight=None, k=2, undir
         propagate_into(buf, F, k, fwd, bwd)
         if not x.is_cuda:
             out[t0:t1] = buf.to(x.device)
+    for op in (fwd, bwd):
+        if op is not None:
+            op.check()
     res = [out[..., b * F:(b + 1) * F] for b in range(nb)]
     return [r[0] for r in res] if squeeze else res
 

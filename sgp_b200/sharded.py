@@ -140,10 +140,11 @@ class RowShardedEncoder:
         csr = ops.Csr(torch.from_numpy(pl.rowptr).to(self.dev), torch.from_numpy(pl.col).to(self.dev),
                       torch.from_numpy(pl.val).to(self.dev), pl.n_own)
         F = encoder.reservoir.num_layers * encoder.reservoir.hidden_size
-        rbu = None
-        if F % 128 == 0 and spat.rbu_mode != "off":
-            rbu = ops.rbu_build(csr, R, grp_rows_h=pl.grp_rows, n_cols=pl.n_own + pl.n_halo)
-        self.op = ShiftOperator(csr, rbu, n_split=pl.n_own)
+        self.op = ShiftOperator(csr, None, n_split=pl.n_own, n_cols=pl.n_own + pl.n_halo)
+        if spat.rbu_mode in ("force16",) and F % 128 == 0:
+            self.op.rbu = ops.rbu_build(csr, R, grp_rows_h=pl.grp_rows, n_cols=pl.n_own + pl.n_halo)
+        else:
+            self.op.maybe_build_rbu(F, spat.rbu_mode)
         self.send_index = torch.from_numpy(pl.send_index).to(self.dev)
         self.send_splits = [int(c) for c in pl.send_counts]
         self.recv_splits = [int(c) for c in pl.recv_counts]

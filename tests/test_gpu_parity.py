@@ -212,6 +212,45 @@ def test_spmm_rbu_irregular_graph_with_duplicates():
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("F", [128, 256, 512])
+@pytest.mark.parametrize("n,k", [(1203, 20), (4000, 100)])
+def test_spmm_tensor_core_vs_oracle(F, n, k):
+    """tcgen05 3xTF32 hop: fp32-accurate against the CPU oracle, on a kNN graph whose size is not a
+    multiple of the 64-row group, with more time steps than one CTA's time block."""
+    ei, ew = sensor_knn(n, k, seed=F + n)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    tc = ops.tc_build(op.csr)
+    assert tc.fill > 0.05
+    rowptr, col, val = O.build_operator(ei, ew, n, set_diag=False)
+    T = 11 if F == 128 else 5
+    x = np.random.default_rng(F).standard_normal((T, n, F)).astype(np.float32)
+    buf = torch.zeros(T, n, 2 * F, device=DEV)
+    buf[..., :F] = torch.from_numpy(x).to(DEV)
+    ops.spmm_tc(tc, buf[..., :F], buf[..., F:])
+    ops.tc_check(tc)
+    ref = O.spmm(rowptr, col, val, x, impl="c")
+    assert_blocks_close(buf[..., F:].cpu().numpy(), ref, F)
+    chk = torch.empty(T, n, F, device=DEV)
+    ops.spmm(op.csr, buf[..., :F], chk)
+    err = float((buf[..., F:] - chk).abs().max() / chk.abs().max())
+    assert err < 2e-5, err
+
+
+def test_spmm_tensor_core_irregular_graph_empty_rows_duplicates():
+    n = 700
+    ei, ew = random_graph(n, 5000, seed=3)
+    keep = (ei[1] % 7) != 3                                        # many empty rows
+    ei, ew = ei[:, keep], ew[keep]
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    tc = ops.tc_build(op.csr)
+    x = torch.randn(3, n, 256, device=DEV)
+    a, b = torch.full_like(x, float("nan")), torch.empty_like(x)
+    ops.spmm_tc(tc, x, a)
+    ops.tc_check(tc)
+    ops.spmm(op.csr, x, b)
+    assert float((a - b).abs().max()) < 2e-5 * float(b.abs().max())
+
+
 def test_khop_chain_fills_blocks_in_place():
     n, F, K = 97, 128, 3
     ei, ew = random_graph(n, 800, seed=2)
@@ -240,6 +279,11 @@ def test_row_stochastic_property_full_size_rows():
     out2 = torch.empty_like(ones)
     op.apply(ones, out2)
     assert float((out2 - 1).abs().max()) < 1e-5
+    tc = ops.tc_build(op.csr)
+    out3 = torch.empty_like(ones)
+    ops.spmm_tc(tc, ones, out3)
+    ops.tc_check(tc)
+    assert float((out3 - 1).abs().max()) < 1e-5
     # linearity + agreement of the two formats on random data
     x = torch.randn(1, n, 128, device=DEV)
     a, b = torch.empty_like(x), torch.empty_like(x)

@@ -37,7 +37,12 @@ def timeit(fn, reps=5):
 
 
 print("csr            %8.1f us/panel" % timeit(lambda: ops.spmm(op.csr, src, dst)))
-for R in (16, 8):
+tc = ops.tc_build(op.csr)
+us = timeit(lambda: ops.spmm_tc(tc, src, dst))
+ops.tc_check(tc)
+print(f"tcgen05 R=64 fill={tc.fill:.3f}  {us:8.1f} us/panel  {flops / us / 1e6:6.2f} TF/s useful  "
+      f"alg {(8 * op.csr.nnz + 8 * N * H) / us / 1e3:7.1f} GB/s  err={float((dst - ref).abs().max() / ref.abs().max()):.2e}")
+for R in (16,):
     for ver, minb, tspan in [(1, 4, 0), (2, 4, 2), (2, 3, 2), (3, 4, 2), (3, 4, 4)]:
         if R == 8 and minb == 3:
             continue
