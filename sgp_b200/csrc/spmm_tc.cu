@@ -43,17 +43,23 @@ namespace sgp {
 
 constexpr int kTcR = 64;            // rows per group  (MMA N)
 constexpr int kTcKC = 32;           // union columns per chunk
-constexpr int kTcAcc = 8;           // accumulators per CTA (time steps x feature chunks)
-constexpr int kTcProducerWarps = 4; // gather (cp.async) warps
-constexpr int kTcSplitGroups = 2;   // split groups alternate items (a even / a odd)
+constexpr int kTcAcc = 4;           // accumulators per CTA (time steps x feature chunks)
+constexpr int kTcABufs = 4;         // A (hi | lo) tiles resident in TMEM
+constexpr int kTcSplitGroups = 2;   // split groups alternate items
 constexpr int kTcSplitWarps = 4 * kTcSplitGroups;   // lo-pass + epilogue warps (warp & 3 = TMEM lane quarter)
+constexpr int kTcProducerWarps = 4; // gather (cp.async) warps
 constexpr int kTcThreads = (kTcSplitWarps + kTcProducerWarps + 1) * 32;   // + 1 MMA-issuing warp
 constexpr int kTcLag = 5;           // cp.async groups a producer thread keeps in flight
-constexpr int kTcStages = 8;        // gathered-row ring (the raw fp32 rows ARE the tf32 "hi" operand)
+constexpr int kTcStages = 8;        // gathered-row ring in shared memory
 constexpr int kTcStageBytes = kTcKC * 128 * 4;      // 16 KB: 32 rows x 128 features
 constexpr int kTcBBytes = 2 * kTcR * kTcKC * 4;     // 16 KB: hi + lo image of one chunk
-constexpr int kTcLoTiles = 4;       // A-lo tiles: the lo pass runs up to 4 items ahead of the tensor pipe
-constexpr size_t kTcSmem = (size_t)kTcStages * kTcStageBytes + kTcLoTiles * kTcStageBytes + 2 * kTcBBytes + 1024;
+constexpr int kTcBBufs = 3;         // slab-image buffers (3: a producer may only wait on MMAs >= 3 chunks old,
+                                    // anything newer can depend on items it has not signalled yet)
+constexpr size_t kTcSmem = (size_t)kTcStages * kTcStageBytes + kTcBBufs * kTcBBytes + 1024;
+// TMEM columns: [0, 256) four fp32 accumulators of 64 columns, [256, 512) four A tiles of
+// (32 hi + 32 lo) columns
+constexpr int kTcTmemCols = 512;
+constexpr int kTcAOff = kTcAcc * kTcR;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,6 +77,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+
+// L2 eviction policies: slab images and the hop's output stream through L2 once (evict_first) so
+// that they do not push out the gathered panel rows, which neighbouring groups re-read (the
+// cross-ring reuse distance of the breadth-first group order is about one wave of CTAs).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 // elect.sync: exactly one lane of a converged warp.  ptxas knows a single lane is active under this
@@ -127,254 +147,314 @@ __device__ __forceinline__ int a_stage_offset(int k, int q) {
     return ((k >> 2) * 4 + (q >> 3)) * 512 + r * 128 + ((((ch >> 1) ^ r) << 5) | ((ch & 1) << 4));
 }
 
-// Warp roles: warps 0-3 "split" (lo pass, then the TMEM epilogue: warp w owns TMEM lanes 32w..),
-// warps 4-7 "producer" (cp.async gathers + slab images), warp 8 issues the MMAs.
-// mbarriers: full[s]  producers -> split/MMA  : stage s holds item i's gathered rows (+ B images)
-//            ready[b] split     -> MMA        : lo tile b written and fenced for the tensor proxy
-//            empty[s] MMA (tcgen05.commit) -> producers : the MMAs reading stage s have completed
-//            lofree[b] MMA (tcgen05.commit) -> split    : the MMAs reading lo tile b have completed
+#define SGP_TMEM_ST32(addr, arr)                                                                   \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,"  \
+                 "%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"       \
+                 :: "r"(addr), "r"(arr[0]), "r"(arr[1]), "r"(arr[2]), "r"(arr[3]), "r"(arr[4]), "r"(arr[5]),  \
+                    "r"(arr[6]), "r"(arr[7]), "r"(arr[8]), "r"(arr[9]), "r"(arr[10]), "r"(arr[11]),            \
+                    "r"(arr[12]), "r"(arr[13]), "r"(arr[14]), "r"(arr[15]), "r"(arr[16]), "r"(arr[17]),        \
+                    "r"(arr[18]), "r"(arr[19]), "r"(arr[20]), "r"(arr[21]), "r"(arr[22]), "r"(arr[23]),        \
+                    "r"(arr[24]), "r"(arr[25]), "r"(arr[26]), "r"(arr[27]), "r"(arr[28]), "r"(arr[29]),        \
+                    "r"(arr[30]), "r"(arr[31]) : "memory")
+
+// Warp roles (13 warps): warps 0-7 "split" in two groups of four that alternate items (warp & 3 =
+// the TMEM lane quarter the warp may touch), warps 8-11 "producer" (cp.async gathers + slab
+// images), warp 12 issues the MMAs.
+// An item is (chunk c, accumulator a); i = 4c + a; ring stage s = i % 8; A tile = a.
+// mbarriers: full[s]  producers -> split  : stage s holds item i's gathered rows (+ slab images)
+//            empty[s] split -> producers  : the split group has copied stage s into TMEM
+//            ready[a] split -> MMA        : A tile a (hi | lo) is in TMEM
+//            afree[a] MMA (tcgen05.commit) -> split : the MMAs reading A tile a have completed
+//            bfree[c%3] MMA (tcgen05.commit) -> producers : slab buffer may be overwritten
 //            done     MMA -> epilogue
-// An item is (chunk c, accumulator a): with 8 ring stages and 8 accumulators per chunk the stage
-// index IS the accumulator index, so the 8 items of a chunk are fully unrolled and every stage
-// address, barrier parity, time step and feature chunk of an item is a compile-time constant.
-// (A single warp runs a dependent instruction chain at ~5 cycles per instruction: the per-item
-// instruction count of each role, not memory or the tensor pipe, was what bounded this kernel.)
+// BOTH MMA operands' A side lives in TMEM: the split warps read a gathered stage once from shared
+// memory (thread = feature = TMEM lane, 32 k values), form hi / lo in registers and tcgen05.st
+// them; the 12 MMAs of an item then fetch only the 2 KB slab operand from shared memory each, so
+// shared-memory bandwidth (the limit of the all-in-smem version: 120 KB per item) drops to 56 KB.
 template <int NFC, bool HALO>
 __global__ void __launch_bounds__(kTcThreads, 1)
 spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ grp_rows,
                    const int32_t* __restrict__ cols, const float* __restrict__ bimg,
+                   int n_groups, int n_work,
                    const float* __restrict__ src, int64_t s_ts, uint32_t s_nb /* row stride, BYTES */,
                    const float* __restrict__ src2, int64_t s2_ts, uint32_t s2_nb, int n_split,
-                   float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int Tc, int* err) {
-    static_assert(kTcStages == kTcAcc && kTcLoTiles == 4, "stage index == accumulator index; lo tile = a & 3");
+                   float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int Tc, int* err, long long* trace) {
+    static_assert(kTcAcc == 4 && kTcABufs == 4 && kTcStages == 8, "index arithmetic below");
     constexpr int TB = kTcAcc / NFC;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-window address
-    __shared__ uint64_t full[kTcStages], empty[kTcStages], ready[kTcLoTiles], lofree[kTcLoTiles], done;
+    __shared__ uint64_t full[kTcStages], empty[kTcStages], ready[kTcABufs], afree[kTcABufs], bfree[kTcBBufs];
+    __shared__ uint64_t done, accfree[kTcAcc];
     __shared__ uint32_t tmem_base_s;
-    __shared__ int rows_s[kTcR];
     __shared__ volatile int abort_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x;
-    const int t_begin = blockIdx.y * TB;
-    const int c_beg = chunk_ptr[g], n_chunks = chunk_ptr[g + 1] - c_beg;
+    // optional per-item timestamps of CTA 7 (tools/trace_tc.py); trace == nullptr in production
+    const bool tr = trace && blockIdx.x == 7;
+#define SGP_TRACE(role, i) do { if (tr && lane == 0 && (i) < 512) trace[(role) * 512 + (i)] = clock64(); } while (0)
 
-    if (n_chunks == 0) {                   // group without stored entries: its rows are zero
-        for (int a = 0; a < kTcAcc; ++a) {
-            const int t = t_begin + a / NFC, fc = a % NFC;
-            if (t >= Tc) continue;
-            for (int i = tid; i < kTcR * 32; i += kTcThreads) {
-                const int row = grp_rows[(size_t)g * kTcR + (i >> 5)];
-                if (row >= 0)
-                    st_f4(dst + (size_t)t * d_ts + (size_t)row * d_ns + fc * 128 + (i & 31) * 4,
-                          make_float4(0.f, 0.f, 0.f, 0.f));
-            }
-        }
-        return;
-    }
-
-    if (tid < kTcR) rows_s[tid] = grp_rows[(size_t)g * kTcR + tid];
     if (tid == 0) {
         abort_s = 0;
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(&full[s], kTcProducerWarps);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], 4);
         }
-        for (int b = 0; b < kTcLoTiles; ++b) {
+        for (int b = 0; b < kTcABufs; ++b) {
             mbar_init(&ready[b], 4);
-            mbar_init(&lofree[b], 1);
+            mbar_init(&afree[b], 1);
+            mbar_init(&accfree[b], 4);
         }
+        for (int b = 0; b < kTcBBufs; ++b) mbar_init(&bfree[b], 1);
         mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(&tmem_base_s)), "r"(kTcAcc * kTcR));
+                     :: "r"(smem_u32(&tmem_base_s)), "r"(kTcTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
-    constexpr uint32_t kLoOff = kTcStages * kTcStageBytes;              // lo tiles after the ring
-    constexpr uint32_t kBOff = (kTcStages + kTcLoTiles) * kTcStageBytes;         // slab images after them
+    constexpr uint32_t kBOff = kTcStages * kTcStageBytes;               // slab images after the ring
 
+    // The CTA is persistent: work item w = (time block y, group g), w = y * n_groups + g, taken
+    // round-robin (w = blockIdx.x, + gridDim.x, ...) so that concurrently running CTAs work on
+    // neighbouring groups of the same time block.  All barrier phases run on counters that
+    // continue across work items: `it` items, `cc` chunks, (bi, bph) slab buffers, `wn` work
+    // items with at least one chunk.  The producers simply run on into the next work item while
+    // the split warps drain the accumulators of the previous one.
     if (warp >= kTcSplitWarps && warp < kTcSplitWarps + kTcProducerWarps) {
-        // ================= producers: item (c, a) -> ring stage a ==============================
+        // ================= producers: item `it` -> ring stage it % 8 ===========================
         const int pw = warp - kTcSplitWarps, ptid = tid - kTcSplitWarps * 32;
         constexpr int kRowsPerWarp = kTcKC / kTcProducerWarps;       // 8 gathered rows per warp per item
         uint32_t dst_off[kRowsPerWarp];                              // swizzled byte offset of my 16 B
 #pragma unroll
         for (int j = 0; j < kRowsPerWarp; ++j)
             dst_off[j] = smem_base + a_stage_offset(pw + j * kTcProducerWarps, lane);
-        // per-accumulator source bases (time step, feature chunk; out-of-range steps clamped)
-        auto base_of = [&](const float* sbase, int64_t ts, int a) -> const char* {
-            const int t = min(t_begin + a / NFC, Tc - 1);
-            return reinterpret_cast<const char*>(sbase + (size_t)t * ts + (a % NFC) * 128 + lane * 4);
-        };
         uint32_t off1[kRowsPerWarp];      // byte offset of each of my rows inside its source
         bool in2[kRowsPerWarp];
-        int colr[kRowsPerWarp];
-        auto load_cols = [&](int c) {
+        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+        int it = 0, bi = 0, bph = 0;
+        bool ok = true;
+        // source-row ids of the NEXT chunk are fetched while the current chunk is being issued
+        int coln[kRowsPerWarp];
+        auto fetch_cols = [&](long long chunk) {
 #pragma unroll
             for (int j = 0; j < kRowsPerWarp; ++j)
-                colr[j] = (c < n_chunks) ? __ldg(cols + (size_t)(c_beg + c) * kTcKC + pw + j * kTcProducerWarps) : 0;
+                coln[j] = __ldg(cols + (size_t)chunk * kTcKC + pw + j * kTcProducerWarps);
         };
-        load_cols(0);
-        // Completion is signalled per WARP and kTcLag items late: a thread keeps kTcLag cp.async
-        // groups in flight, waits for the oldest one, and lane 0 arrives on that item's barrier.
-        bool ok = true;
-        for (int c = 0; c < n_chunks + 1 && ok; ++c) {
-            if (c < n_chunks) {
+        auto first_chunk_of = [&](int w) -> long long {        // first chunk of the next non-empty work item
+            for (; w < n_work; w += gridDim.x) {
+                const int g2 = w % n_groups;
+                if (chunk_ptr[g2 + 1] > chunk_ptr[g2]) return chunk_ptr[g2];
+            }
+            return -1;
+        };
+        {
+            const long long f = first_chunk_of(blockIdx.x);
+            if (f >= 0) fetch_cols(f);
+        }
+        for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
+            const int g = w % n_groups, t_begin = (w / n_groups) * TB;
+            const int c_beg = chunk_ptr[g], n_chunks = chunk_ptr[g + 1] - c_beg;
+            auto base_of = [&](const float* sbase, int64_t ts, int a) -> const char* {
+                const int t = min(t_begin + a / NFC, Tc - 1);      // out-of-range steps are clamped
+                return reinterpret_cast<const char*>(sbase + (size_t)t * ts + (a % NFC) * 128 + lane * 4);
+            };
+            for (int c = 0; c < n_chunks && ok; ++c) {
 #pragma unroll
                 for (int j = 0; j < kRowsPerWarp; ++j) {
-                    in2[j] = HALO && colr[j] >= n_split;
-                    off1[j] = in2[j] ? (uint32_t)(colr[j] - n_split) * s2_nb : (uint32_t)colr[j] * s_nb;
+                    const int col = coln[j];
+                    in2[j] = HALO && col >= n_split;
+                    off1[j] = in2[j] ? (uint32_t)(col - n_split) * s2_nb : (uint32_t)col * s_nb;
                 }
-                load_cols(c + 1);          // next chunk's row ids: in flight during this chunk
-            }
+                {
+                    const long long nxt = (c + 1 < n_chunks) ? (long long)(c_beg + c + 1) : first_chunk_of(w + gridDim.x);
+                    if (nxt >= 0) fetch_cols(nxt);
+                }
 #pragma unroll 1
-            for (int a = 0; a < kTcAcc; ++a) {
-                if (c < n_chunks) {
-                    if (c > 0 && !warp_wait(&empty[a], (c - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
+                for (int a = 0; a < kTcAcc; ++a, ++it) {
+                    const int s = it & (kTcStages - 1);
+                    if (it >= kTcStages && !warp_wait(&empty[s], ((it >> 3) + 1) & 1, &abort_s, err, lane)) { ok = false; break; }
+                    if (pw == 0) SGP_TRACE(0, it);
                     const char* b1 = base_of(src, s_ts, a);
                     const char* b2 = HALO ? base_of(src2, s2_ts, a) : nullptr;
 #pragma unroll
                     for (int j = 0; j < kRowsPerWarp; ++j) {
                         const char* p = (HALO && in2[j]) ? b2 + off1[j] : b1 + off1[j];
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-                                     :: "r"(dst_off[j] + a * kTcStageBytes), "l"(p));
+                        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n"
+                                     :: "r"(dst_off[j] + s * kTcStageBytes), "l"(p), "l"(pol_keep));
                     }
-                    if (a == 0) {   // the chunk's slab images (hi | lo), reused by its 8 items
+                    if (a == 0) {   // the chunk's slab images (hi | lo), reused by its 4 items
+                        if (bph > 0 && !warp_wait(&bfree[bi], (bph - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
                         const float* bs = bimg + (size_t)(c_beg + c) * (kTcBBytes / 4);
-                        const uint32_t bd = smem_base + kBOff + (c & 1) * kTcBBytes;
+                        const uint32_t bd = smem_base + kBOff + bi * kTcBBytes;
+                        if (++bi == kTcBBufs) { bi = 0; ++bph; }
 #pragma unroll
                         for (int j = 0; j < kTcBBytes / 16 / (kTcProducerWarps * 32); ++j)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n"
                                          :: "r"(bd + (j * kTcProducerWarps * 32 + ptid) * 16),
-                                            "l"(bs + (j * kTcProducerWarps * 32 + ptid) * 4));
+                                            "l"(bs + (j * kTcProducerWarps * 32 + ptid) * 4), "l"(pol_stream));
+                    }
+                    cp_async_commit();
+                    if (it >= kTcLag) {          // signal item it - kTcLag (kTcLag groups stay in flight)
+                        cp_async_wait<kTcLag>();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[(it - kTcLag) & (kTcStages - 1)]);
+                        if (pw == 0) SGP_TRACE(1, it - kTcLag);
                     }
                 }
-                cp_async_commit();
-                // signal the item issued kTcLag commits ago: (c, a - kTcLag) or (c - 1, a - kTcLag + 8)
-                if (c > 0 || a >= kTcLag) {
-                    cp_async_wait<kTcLag>();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[(a + kTcAcc - kTcLag) % kTcAcc]);
-                }
-                if (c == n_chunks && a == kTcLag - 1) break;      // drained: all items signalled
             }
         }
+        // drain: signal the last kTcLag items
         cp_async_wait<0>();
+        __syncwarp();
+        if (ok && lane == 0)
+            for (int j = max(it - kTcLag, 0); j < it; ++j) mbar_arrive(&full[j & (kTcStages - 1)]);
     } else if (warp < kTcSplitWarps) {
-        // ================= split warps: lo = x - tf32(x), then the epilogue =====================
-        // two groups of 4 warps; group G takes the items with (a & 1) == G, so a group has two item
-        // periods for its waits + lo pass and the tensor pipe is never the one that waits
-        const int grp = warp >> 2, gtid = tid & 127;
+        // ================= split warps: stage (smem) -> A hi | lo tiles (TMEM); epilogue =======
+        // two groups of 4 warps; group G takes the items / accumulators with (a & 1) == G
+        const int grp = warp >> 2, m = tid & 127;                  // m = feature = TMEM lane
+        const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+        const int q = m >> 2, e = m & 3;                           // 16-byte piece / element of feature m
+        const uint64_t pol_stream = l2_policy_evict_first();
+        int it0 = 0, cc = 0, wn = 0;                               // items, chunks, non-empty work items so far
         bool ok = true;
-        for (int c = 0; c < n_chunks && ok; ++c) {
+        for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
+            const int g = w % n_groups, t_begin = (w / n_groups) * TB;
+            const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
+            for (int c = 0; c < n_chunks && ok; ++c, ++cc, it0 += kTcAcc) {
 #pragma unroll 1
-            for (int a = grp; a < kTcAcc; a += kTcSplitGroups) {
-                const int b = a & (kTcLoTiles - 1);
-                if (!warp_wait(&full[a], c & 1, &abort_s, err, lane)) { ok = false; break; }
-                if ((c > 0 || a >= kTcLoTiles) && !warp_wait(&lofree[b], ((a >> 2) + 1) & 1, &abort_s, err, lane)) { ok = false; break; }
-                const uint32_t rs = smem_base + a * kTcStageBytes + gtid * 16;
-                const uint32_t lo = smem_base + kLoOff + b * kTcStageBytes + gtid * 16;
-                float4 v[kTcStageBytes / 16 / 128];
+                for (int a = grp; a < kTcAcc; a += kTcSplitGroups) {
+                    const int it = it0 + a, s = it & (kTcStages - 1);
+                    if (!warp_wait(&full[s], (it >> 3) & 1, &abort_s, err, lane)) { ok = false; break; }
+                    if ((warp & 3) == 0) SGP_TRACE(2, it);
+                    if (cc > 0 && !warp_wait(&afree[a], (cc - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
+                    if ((warp & 3) == 0) SGP_TRACE(3, it);
+                    const uint32_t rs = smem_base + s * kTcStageBytes + (q >> 3) * 512 + e * 4;
+                    uint32_t hv[kTcKC], lv[kTcKC];
 #pragma unroll
-                for (int j = 0; j < kTcStageBytes / 16 / 128; ++j)
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                 : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w)
-                                 : "r"(rs + j * 128 * 16));
-#pragma unroll
-                for (int j = 0; j < kTcStageBytes / 16 / 128; ++j) {
-                    float4 l;
-                    l.x = v[j].x - __uint_as_float(__float_as_uint(v[j].x) & 0xffffe000u);
-                    l.y = v[j].y - __uint_as_float(__float_as_uint(v[j].y) & 0xffffe000u);
-                    l.z = v[j].z - __uint_as_float(__float_as_uint(v[j].z) & 0xffffe000u);
-                    l.w = v[j].w - __uint_as_float(__float_as_uint(v[j].w) & 0xffffe000u);
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
-                                 :: "r"(lo + j * 128 * 16), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
-                                 : "memory");
+                    for (int k = 0; k < kTcKC; ++k) {
+                        const int r = k & 3, ch = q & 7;
+                        const uint32_t off = (k >> 2) * 2048 + r * 128 + ((((ch >> 1) ^ r) << 5) | ((ch & 1) << 4));
+                        float x;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(rs + off));
+                        hv[k] = __float_as_uint(x);        // the tensor core ignores the low 13 mantissa bits
+                        lv[k] = __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+                    }
+                    const uint32_t ta = lane_addr + kTcAOff + a * 64;
+                    SGP_TMEM_ST32(ta, hv);
+                    SGP_TMEM_ST32(ta + 32, lv);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&ready[a]);
+                        mbar_arrive(&empty[s]);
+                    }
+                    if ((warp & 3) == 0) SGP_TRACE(4, it);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // lo tile (and, by cumulativity,
-                __syncwarp();                                                  // the gathered stage) -> tensor proxy
-                if (lane == 0) mbar_arrive(&ready[b]);
             }
-        }
-        if (ok) ok = warp_wait(&done, 0, &abort_s, err, lane);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (ok) {
-            // thread = TMEM lane = feature; 8 accumulators x 64 row columns
-            const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+            if (!ok) break;
+            // ---- epilogue of this work item: thread = TMEM lane = feature; my group's accumulators
+            if (n_chunks > 0) {
+                if (!warp_wait(&done, wn & 1, &abort_s, err, lane)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
 #pragma unroll 1
             for (int a = grp; a < kTcAcc; a += kTcSplitGroups) {
                 const int t = t_begin + a / NFC;
-                if (t >= Tc) continue;
-                float* dp = dst + (size_t)t * d_ts + (a % NFC) * 128 + (warp & 3) * 32 + lane;
+                float* dp = dst + (size_t)min(t, Tc - 1) * d_ts + (a % NFC) * 128 + (warp & 3) * 32 + lane;
 #pragma unroll
                 for (int j = 0; j < kTcR; j += 16) {
                     uint32_t v[16];
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
-                                   "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
-                                   "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                                 : "r"(taddr + a * kTcR + j));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (n_chunks > 0) {
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                                       "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                                       "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                     : "r"(lane_addr + a * kTcR + j));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int row = rows_s[j + e];
-                        if (row >= 0) dp[(size_t)row * d_ns] = __uint_as_float(v[e]);
+                        for (int e2 = 0; e2 < 16; ++e2) v[e2] = 0u;      // group without entries: zero rows
+                    }
+                    if (t < Tc) {
+#pragma unroll
+                        for (int e2 = 0; e2 < 16; ++e2) {
+                            const int row = __ldg(grp_rows + (size_t)g * kTcR + j + e2);
+                            if (row >= 0)
+                                asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(dp + (size_t)row * d_ns), "r"(v[e2]), "l"(pol_stream) : "memory");
+                        }
                     }
                 }
+                if (n_chunks > 0) {       // accumulator a may be overwritten by the next work item
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accfree[a]);
+                }
             }
+            if (n_chunks > 0) ++wn;
         }
     } else {
-        // ================= MMA issuer: the whole warp runs the loop, one lane issues ==========
-        // kind::tf32, fp32 accumulate, A M-major (gathered rows), B K-major, N = 64, M = 128
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
+        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues ===
+        // kind::tf32, fp32 accumulate, A from TMEM (lane = feature, column = k), B K-major smem,
+        // N = 64, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
                                    ((uint32_t)(kTcR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        // descriptors differ only in their 14-bit start-address field
-        constexpr uint32_t a_hi32 = (2048u >> 4) | (1u << 14) | (1u << 29);   // SBO, version, SW128_BASE32B
         constexpr uint32_t b_hi32 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SW128
-        constexpr uint32_t a_lo32 = (512u >> 4) << 16, b_lo32 = (16u >> 4) << 16;   // LBO
+        constexpr uint32_t b_lo32 = (16u >> 4) << 16;                          // LBO
         auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
-        const uint32_t raw0 = a_lo32 | (smem_base >> 4);
-        const uint32_t lo0 = a_lo32 | ((smem_base + kLoOff) >> 4);
+        auto mma_ts = [](uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc_, uint32_t acc) {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                         :: "r"(d), "r"(a_tmem), "l"(db), "r"(idesc_), "r"(acc) : "memory");
+        };
         const uint32_t bb0 = b_lo32 | ((smem_base + kBOff) >> 4);
+        int bi = 0, cc = 0, wn = 0, itn = 0;
         bool ok = true;
-        for (int c = 0; c < n_chunks && ok; ++c) {
-            const uint32_t bh = bb0 + (c & 1) * (kTcBBytes >> 4), bl = bh + (kTcBBytes >> 5);
+        for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
+            const int g = w % n_groups;
+            const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
+            for (int c = 0; c < n_chunks && ok; ++c, ++cc) {
+                const uint32_t bh = bb0 + bi * (kTcBBytes >> 4), bl = bh + (kTcBBytes >> 5);
 #pragma unroll 1
-            for (int a = 0; a < kTcAcc; ++a) {
-                const int b = a & (kTcLoTiles - 1);
-                if (!warp_wait(&ready[b], (a >> 2) & 1, &abort_s, err, lane)) { ok = false; break; }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t ah = raw0 + a * (kTcStageBytes >> 4);
-                    const uint32_t al = lo0 + b * (kTcStageBytes >> 4);
-                    const uint32_t d = tmem_d + a * kTcR;
+                for (int a = 0; a < kTcAcc; ++a, ++itn) {
+                    if (!warp_wait(&ready[a], cc & 1, &abort_s, err, lane)) { ok = false; break; }
+                    // first MMA into accumulator a of this work item: the previous one must be drained
+                    if (c == 0 && wn > 0 && !warp_wait(&accfree[a], (wn - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
+                    SGP_TRACE(5, itn);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint32_t ah = tmem_d + kTcAOff + a * 64, al = ah + 32;
+                        const uint32_t d = tmem_d + a * kTcR;
 #pragma unroll
-                    for (int ks = 0; ks < kTcKC / 8; ++ks) {
-                        const uint64_t dah = desc(ah + ks * 256, a_hi32), dal = desc(al + ks * 256, a_hi32);
-                        const uint64_t dbh = desc(bh + ks * 2, b_hi32), dbl = desc(bl + ks * 2, b_hi32);
-                        umma_tf32(d, dah, dbh, idesc, (c | ks) ? 1u : 0u);
-                        umma_tf32(d, dal, dbh, idesc, 1u);
-                        umma_tf32(d, dah, dbl, idesc, 1u);
+                        for (int ks = 0; ks < kTcKC / 8; ++ks) {
+                            const uint64_t dbh = desc(bh + ks * 2, b_hi32), dbl = desc(bl + ks * 2, b_hi32);
+                            mma_ts(d, ah + ks * 8, dbh, idesc, (c | ks) ? 1u : 0u);
+                            mma_ts(d, al + ks * 8, dbh, idesc, 1u);
+                            mma_ts(d, ah + ks * 8, dbl, idesc, 1u);
+                        }
+                        umma_commit(&afree[a]);                          // A tile a may be rewritten
+                        if (a == kTcAcc - 1) {
+                            umma_commit(&bfree[bi]);                      // slab buffer may be refilled
+                            if (c == n_chunks - 1) umma_commit(&done);    // accumulators complete
+                        }
                     }
-                    umma_commit(&empty[a]);      // ring stage a may be refilled
-                    umma_commit(&lofree[b]);     // lo tile b may be rewritten
+                    __syncwarp();
+                    SGP_TRACE(6, itn);
                 }
-                __syncwarp();
+                if (++bi == kTcBBufs) bi = 0;
             }
+            if (n_chunks > 0) ++wn;
         }
-        if (ok && elect_one()) umma_commit(&done);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(kTcAcc * kTcR));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(kTcTmemCols));
 }
 
 }  // namespace sgp
@@ -389,8 +469,8 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
     SGP_REQUIRE(chunk_ptr && grp_rows && cols && bimg && src && dst && err_flag, SGP_EINVAL,
                 "sgp_spmm_rbu_tc: null pointer");
     const int nfc = F / 128;
-    SGP_REQUIRE(F % 128 == 0 && (nfc == 1 || nfc == 2 || nfc == 4 || nfc == 8), SGP_EUNSUPPORTED,
-                "sgp_spmm_rbu_tc: F=%d (128, 256, 512 or 1024)", F);
+    SGP_REQUIRE(F % 128 == 0 && (nfc == 1 || nfc == 2 || nfc == 4), SGP_EUNSUPPORTED,
+                "sgp_spmm_rbu_tc: F=%d (128, 256 or 512)", F);
     SGP_REQUIRE(aligned16(src) && aligned16(dst) && aligned16(bimg) && src_t_stride % 4 == 0 &&
                     src_n_stride % 4 == 0 && (!src2 || (aligned16(src2) && src2_t_stride % 4 == 0 &&
                                                         src2_n_stride % 4 == 0)),
@@ -404,21 +484,21 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
     SGP_REQUIRE(src_n_stride > 0 && src_n_stride * 4 < (1ll << 31) / 64 && (!src2 || (src2_n_stride > 0 && src2_n_stride * 4 < (1ll << 31) / 64)),
                 SGP_EUNSUPPORTED, "sgp_spmm_rbu_tc: row stride too large");
     const uint32_t s_nb = (uint32_t)(src_n_stride * 4), s2_nb = (uint32_t)(src2_n_stride * 4);
-    dim3 grid((unsigned)n_groups, ny);
+    const int n_work = n_groups * ny;
+    const int grid = n_work < kNumSMs ? n_work : kNumSMs;        // persistent: one CTA per SM
+    long long* trace_ptr = getenv("SGP_B200_TC_TRACE") ? (long long*)strtoull(getenv("SGP_B200_TC_TRACE"), nullptr, 10) : nullptr;
 #define SGP_TC(NFC_, HALO_)                                                                            \
     do {                                                                                               \
         SGP_CUDA(cudaFuncSetAttribute(spmm_rbu_tc_kernel<NFC_, HALO_>,                                 \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));     \
         spmm_rbu_tc_kernel<NFC_, HALO_><<<grid, kTcThreads, kTcSmem, as_stream(stream)>>>(             \
-            chunk_ptr, grp_rows, cols, bimg, src, src_t_stride, s_nb, src2, src2_t_stride, s2_nb,      \
-            n_split, dst, dst_t_stride, dst_n_stride, Tc, err_flag);                                \
+            chunk_ptr, grp_rows, cols, bimg, n_groups, n_work, src, src_t_stride, s_nb, src2,          \
+            src2_t_stride, s2_nb, n_split, dst, dst_t_stride, dst_n_stride, Tc, err_flag, trace_ptr);  \
     } while (0)
     if (src2) {
-        if (nfc == 1) SGP_TC(1, true); else if (nfc == 2) SGP_TC(2, true);
-        else if (nfc == 4) SGP_TC(4, true); else SGP_TC(8, true);
+        if (nfc == 1) SGP_TC(1, true); else if (nfc == 2) SGP_TC(2, true); else SGP_TC(4, true);
     } else {
-        if (nfc == 1) SGP_TC(1, false); else if (nfc == 2) SGP_TC(2, false);
-        else if (nfc == 4) SGP_TC(4, false); else SGP_TC(8, false);
+        if (nfc == 1) SGP_TC(1, false); else if (nfc == 2) SGP_TC(2, false); else SGP_TC(4, false);
     }
 #undef SGP_TC
     SGP_LAUNCH_CHECK("spmm_rbu_tc");

@@ -66,7 +66,7 @@ class ShiftOperator:
         if mode.startswith("force"):
             self.rbu = ops.rbu_build(self.csr, int(mode[len("force"):]), n_cols=self.n_cols)
             return
-        if mode in ("auto", "tc") and (F // 128) in (1, 2, 4, 8):
+        if mode in ("auto", "tc") and (F // 128) in (1, 2, 4):
             cand = ops.tc_build(self.csr, n_cols=self.n_cols)
             if cand.fill >= _TC_MIN_FILL or mode == "tc":
                 self.tc = cand
@@ -83,7 +83,7 @@ class ShiftOperator:
         F = src.size(-1)
         aligned = (F % 128 == 0 and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0 and
                    all(s % 4 == 0 for s in (*src.stride()[:2], *dst.stride()[:2])))
-        if self.tc is not None and aligned and (F // 128) in (1, 2, 4, 8):
+        if self.tc is not None and aligned and (F // 128) in (1, 2, 4):
             ops.spmm_tc(self.tc, src, dst, halo, self.n_split)
         elif self.rbu is not None and aligned:
             ops.spmm_rbu(self.rbu, src, dst, halo, self.n_split)

@@ -12,13 +12,13 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-__global__ void __launch_bounds__(128, 1) rate(int N, int amajor, int iters, long long* out, int distinct) {
+__global__ void __launch_bounds__(128, 1) rate(int N, int amajor, int iters, long long* out, int distinct, int ts) {
     extern __shared__ __align__(1024) uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar; __shared__ uint32_t tb;
     for (int i = threadIdx.x; i < (8 * 16384 + 2 * 32768) / 4; i += 128) ((float*)smem)[i] = 1.0f;
     if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (threadIdx.x < 32) { asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tb)), "r"(256)); asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::); }
+    if (threadIdx.x < 32) { asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tb)), "r"(512)); asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); __syncthreads(); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)amajor << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -31,6 +31,11 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int amajor, int iters, lon
             for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t da = amajor ? make_desc(a + ks * 4096, 512, 2048, 1) : make_desc(a + ks * 32, 16, 1024, 2);
                 const uint64_t db = make_desc(b + ks * 32, 16, 1024, 2);
+                if (ts) {
+                    const uint32_t idts = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                                 :: "r"(tb), "r"(tb + 256 + (distinct ? (it & 3) * 64 : 0) + ks * 8), "l"(db), "r"(idts), "r"(1u) : "memory");
+                } else
                 mma(tb, da, db, idesc, 1u);
             }
         }
@@ -43,20 +48,21 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int amajor, int iters, lon
         out[0] = t1 - t0; out[1] = t2 - t0; out[2] = done;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); __syncthreads();
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tb), "r"(256));
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tb), "r"(512));
 }
 int main() {
     long long* d; cudaMalloc(&d, 32); long long h[3];
     cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    for (int distinct = 0; distinct < 2; ++distinct)
-    for (int amajor = 0; amajor < 2; ++amajor)
+    for (int ts = 0; ts < 2; ++ts)
+    for (int distinct = 1; distinct < 2; ++distinct)
+    for (int amajor = 1; amajor < 2; ++amajor)
         for (int N : {64, 128, 256})
             for (int rep = 0; rep < 2; ++rep) {
                 const int iters = 500;
-                rate<<<1, 128, 198 * 1024>>>(N, amajor, iters, d, distinct);
+                rate<<<1, 128, 198 * 1024>>>(N, amajor, iters, d, distinct, ts);
                 cudaError_t e = cudaDeviceSynchronize();
                 cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
-                if (rep) printf("distinct=%d A %s-major N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (done=%lld, %s)  -> %.0f MAC/clk\n", distinct, amajor ? "M" : "K", N,
+                if (rep) printf("ts=%d distinct=%d A %s-major N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (done=%lld, %s)  -> %.0f MAC/clk\n", ts, distinct, amajor ? "M" : "K", N,
                        (double)h[0] / (iters * 4), (double)h[1] / (iters * 4), h[2], cudaGetErrorString(e), 128.0 * N * 8 / ((double)h[1] / (iters * 4)));
             }
     return 0;

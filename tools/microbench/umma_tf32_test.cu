@@ -52,7 +52,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
 // X: [nchunks*KC][M] fp32 row-major (gathered rows), Bimg: [nchunks][split?2:1][B_STAGE bytes]
 __global__ void __launch_bounds__(128, 1)
 umma_test(const float* __restrict__ X, const float* __restrict__ Bimg, float* __restrict__ D,
-          int nchunks, int split, int* err, int amajor, int prefill) {
+          int nchunks, int split, int* err, int amajor, int prefill, int ts) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* a_hi = smem;                     // A_STAGE
@@ -68,7 +68,7 @@ umma_test(const float* __restrict__ X, const float* __restrict__ Bimg, float* __
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(64));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -123,8 +123,48 @@ umma_test(const float* __restrict__ X, const float* __restrict__ Bimg, float* __
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (ts) {
+            // TS mode: thread = TMEM lane = feature m; read X[k][m] for the chunk's 32 k from the
+            // swizzled stage (hi tile holds raw/hi values), write hi -> cols [64,96), lo -> [96,128)
+            const int m = tid;
+            const uint32_t ta = tmem_d + ((uint32_t)(warp * 32) << 16);
+            uint32_t hv[32], lv[32];
+            for (int k = 0; k < KC; ++k) {
+                const int q = m >> 2, b = q >> 3, ch = q & 7, kg = k >> 2, r = k & 3;
+                const int off = (kg * 4 + b) * 512 + r * 128 + ((((ch >> 1) ^ r) << 5) | ((ch & 1) << 4)) + (m & 3) * 4;
+                const float x = X[(size_t)(c * KC + k) * M + m];   // same value as the staged one
+                (void)off;
+                const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+                hv[k] = __float_as_uint(split ? h : x);
+                lv[k] = __float_as_uint(split ? x - h : 0.f);
+            }
+#define ST32(base, arr) asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" :: "r"(base), "r"(arr[0]),"r"(arr[1]),"r"(arr[2]),"r"(arr[3]),"r"(arr[4]),"r"(arr[5]),"r"(arr[6]),"r"(arr[7]),"r"(arr[8]),"r"(arr[9]),"r"(arr[10]),"r"(arr[11]),"r"(arr[12]),"r"(arr[13]),"r"(arr[14]),"r"(arr[15]),"r"(arr[16]),"r"(arr[17]),"r"(arr[18]),"r"(arr[19]),"r"(arr[20]),"r"(arr[21]),"r"(arr[22]),"r"(arr[23]),"r"(arr[24]),"r"(arr[25]),"r"(arr[26]),"r"(arr[27]),"r"(arr[28]),"r"(arr[29]),"r"(arr[30]),"r"(arr[31]) : "memory")
+            ST32(ta + 64, hv);
+            ST32(ta + 96, lv);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+        }
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (ts) {
+                const uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
+                                          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+                for (int ks = 0; ks < KC / 8; ++ks) {
+                    const uint64_t dbh = make_desc(smem_u32(b_hi) + ks * 32, 16, 1024);
+                    const uint64_t dbl = make_desc(smem_u32(b_lo) + ks * 32, 16, 1024);
+                    const uint32_t ahi = tmem_d + 64 + ks * 8, alo = tmem_d + 96 + ks * 8;
+                    uint32_t acc = (c | ks) ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                                 :: "r"(tmem_d), "r"(ahi), "l"(dbh), "r"(idesc_ts), "r"(acc) : "memory");
+                    if (split) {
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                                     :: "r"(tmem_d), "r"(alo), "l"(dbh), "r"(idesc_ts), "r"(1u) : "memory");
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                                     :: "r"(tmem_d), "r"(ahi), "l"(dbl), "r"(idesc_ts), "r"(1u) : "memory");
+                    }
+                }
+            } else
             for (int ks = 0; ks < KC / 8; ++ks) {
                 const uint64_t dah = amajor ? make_desc(smem_u32(a_hi) + ks * 4096, 512, 2048, 1)
                                             : make_desc(smem_u32(a_hi) + ks * 32, 16, 1024);
@@ -158,7 +198,7 @@ umma_test(const float* __restrict__ X, const float* __restrict__ Bimg, float* __
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(64));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(128));
 }
 
 static void swizzle_b(const std::vector<float>& Bv /*[N][K]*/, int K, int c, float* img) {
@@ -170,7 +210,7 @@ static void swizzle_b(const std::vector<float>& Bv /*[N][K]*/, int K, int c, flo
         }
 }
 
-int run(int nchunks, int split, bool exact_inputs, int amajor = 1, int prefill = 0) {
+int run(int nchunks, int split, bool exact_inputs, int amajor = 1, int prefill = 0, int ts = 0) {
     const int K = nchunks * KC;
     std::vector<float> X((size_t)K * M), Bv((size_t)N * K), Dref((size_t)N * M), Dout((size_t)N * M);
     srand(1234 + nchunks + split);
@@ -203,7 +243,7 @@ int run(int nchunks, int split, bool exact_inputs, int amajor = 1, int prefill =
     cudaMemset(dD, 0xff, Dout.size() * 4); cudaMemset(derr, 0, 4);
     const size_t smem = 2 * A_STAGE + 2 * B_STAGE + 1024;
     cudaFuncSetAttribute(umma_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    umma_test<<<1, 128, smem>>>(dX, dB, dD, nchunks, split, derr, amajor, prefill);
+    umma_test<<<1, 128, smem>>>(dX, dB, dD, nchunks, split, derr, amajor, prefill, ts);
     cudaError_t e = cudaDeviceSynchronize();
     int herr = 0;
     cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost);
@@ -214,7 +254,7 @@ int run(int nchunks, int split, bool exact_inputs, int amajor = 1, int prefill =
         maxref = fmax(maxref, fabs((double)Dref[i]));
     }
     int nz = 0; for (auto v : Dout) nz += (v != 0.f);
-    printf("amajor=%d prefill=%d nonzero=%d ", amajor, prefill, nz);
+    printf("ts=%d amajor=%d prefill=%d nonzero=%d ", ts, amajor, prefill, nz);
     printf("chunks=%d split=%d exact=%d: cuda=%s barrier_timeout=%d max|err|=%.3e (max|ref|=%.3e) rel=%.2e  D[0..3]=%g %g %g %g ref=%g %g %g %g\n",
            nchunks, split, (int)exact_inputs, cudaGetErrorString(e), herr, maxerr, maxref, maxerr / fmax(maxref, 1e-30),
            Dout[0], Dout[1], Dout[2], Dout[3], Dref[0], Dref[1], Dref[2], Dref[3]);
@@ -224,6 +264,10 @@ int run(int nchunks, int split, bool exact_inputs, int amajor = 1, int prefill =
 
 int main() {
     int bad = 0;
+    bad |= run(1, 0, true, 1, 1, 1);
+    bad |= run(3, 0, true, 1, 0, 1);
+    bad |= run(11, 1, false, 1, 0, 1);
+    bad |= run(11, 2, false, 1, 0, 1);
     bad |= run(1, 0, true, 0, 0);
     bad |= run(1, 0, true, 0, 1);
     bad |= run(1, 0, true, 1, 1);
