@@ -227,7 +227,7 @@ def run_own(args, cfg):
     x_dev = torch.from_numpy(x).to(dev)
     ei_dev, ew_dev = torch.from_numpy(ei).to(dev), torch.from_numpy(ew).to(dev)
     fwd, bwd = enc.sgp_encoder.build_operators(ei_dev, ew_dev, N, dev, F)
-    plan = enc.reservoir.device_plan(dev)
+    plan = enc.reservoir.device_plan(dev, N)
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     bufs = [torch.empty(step_T, N, D, device=dev) for _ in range(2)]
     state = torch.zeros(1, N, H, device=dev)
@@ -264,6 +264,7 @@ def run_own(args, cfg):
     launches = _lib.launch_count() - l0
     clocks = sampler.stop()
     fwd.check()
+    enc.reservoir.check_plan(plan)
     ms_step = e0.elapsed_time(e1) / args.steps
     value = N * T / (ms_step * 1e-3)
 
@@ -290,7 +291,7 @@ def run_own(args, cfg):
                     gflops=flops_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0,
                     fp32_fma_peak_tflops=fma_peak,
                     share_of_step=spmm_ms / (spmm_ms + scan_ms) if spmm_ms + scan_ms else None)
-    reservoir = dict(kernel="reservoir_scan_tiled", ms_per_step=scan_ms / args.steps,
+    reservoir = dict(kernel="reservoir_tc_kernel (tcgen05, 3xTF32)" if plan[0][0] == "tc" else "reservoir_scan_tiled", ms_per_step=scan_ms / args.steps,
                      tflops=scan_flops / (scan_ms * 1e-3) / 1e12 if scan_ms else 0.0,
                      frac_of_fp32_fma_peak=(scan_flops / (scan_ms * 1e-3) / 1e12) / fma_peak if scan_ms else 0.0,
                      share_of_step=scan_ms / (spmm_ms + scan_ms) if spmm_ms + scan_ms else None)

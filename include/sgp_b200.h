@@ -97,6 +97,17 @@ int sgp_reservoir_scan(const float* x, int64_t x_t_stride, int64_t x_n_stride, i
                        float* out, int64_t out_t_stride, int64_t out_n_stride,
                        int Tc, int N, int H, void* stream);
 
+/* Tensor-core scan (tcgen05, 3xTF32, fp32-accurate): same contract as sgp_reservoir_scan for
+ * H in {128, 256}, Fin <= 8, activation tanh / relu / identity.  wimg [H*H*2] = W_hh split into tf32
+ * hi / lo images in the kernel's shared-memory layout (sgp_reservoir_tc_pack); w_ih [H, Fin] and bias
+ * [H] as in the reference.  *err_flag (device int) is set to 1 if an internal barrier times out. */
+int sgp_reservoir_tc_pack(const float* w_hh /*[H,H]*/, int H, float* wimg /*[2*H*H]*/, void* stream);
+int sgp_reservoir_scan_tc(const float* x, int64_t x_t_stride, int64_t x_n_stride, int Fin,
+                          const float* wimg, const float* w_ih, const float* bias,
+                          float alpha, float one_minus_alpha, int act,
+                          float* h_state, float* out, int64_t out_t_stride, int64_t out_n_stride,
+                          int Tc, int N, int H, int* err_flag, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2  CSR x dense propagation, batched over the leading (time / batch) axis.
  * Replaces `x = adj @ x` (lib/sgp_preprocessing.py:200-203; torch_sparse spmm_sum):

@@ -169,7 +169,7 @@ class SGPEncoder(nn.Module):
         F, D = L * H, self.output_size
         fwd, bwd = operators if operators is not None else \
             spat.build_operators(edge_index, edge_weight, N, dev, F)
-        plan = res.device_plan(dev)
+        plan = res.device_plan(dev, N)
         step = self.chunk_steps or _chunk_steps(T, N * D * 4)
         state = torch.zeros(L, N, H, device=dev)
         bufs = [torch.empty(step, N, D, device=dev) for _ in range(2 if step < T else 1)]
@@ -184,6 +184,7 @@ class SGPEncoder(nn.Module):
         for op in (fwd, bwd):
             if op is not None:
                 op.check()
+        res.check_plan(plan)
 
     def forward(self, x, edge_index, edge_weight):
         """x [T, N, Fin] on CPU or GPU -> [T, N, D] on the same device."""
@@ -237,7 +238,7 @@ class SGPTemporalEncoder(nn.Module):
         dev = _cuda_device_for(x)
         res = self.reservoir
         L, H = res.num_layers, res.hidden_size
-        plan = res.device_plan(dev)
+        plan = res.device_plan(dev, N)
         out = torch.empty(T, N, L * H, dtype=torch.float32, device=x.device)
         state = torch.zeros(L, N, H, device=dev)
         step = T if x.is_cuda else _chunk_steps(T, N * L * H * 4)
@@ -247,6 +248,7 @@ class SGPTemporalEncoder(nn.Module):
             res.scan_chunk(plan, x[t0:t1].detach().to(device=dev, dtype=torch.float32), state, buf)
             if not x.is_cuda:
                 out[t0:t1] = buf.to(x.device)
+        res.check_plan(plan)
         return out
 
     @staticmethod

@@ -103,6 +103,33 @@ def reservoir_scan(x: torch.Tensor, wpack: torch.Tensor, bias: torch.Tensor, alp
                                     _stream(x.device)), "sgp_reservoir_scan")
 
 
+def reservoir_tc_pack(w_hh: torch.Tensor) -> torch.Tensor:
+    """W_hh [H, H] -> tf32 hi / lo images for the tensor-core scan (H in {128, 256})."""
+    _require_cuda(w_hh)
+    H = int(w_hh.shape[0])
+    out = torch.empty(2 * H * H, dtype=torch.float32, device=w_hh.device)
+    check(load().sgp_reservoir_tc_pack(_p(w_hh.contiguous()), H, _p(out), _stream(w_hh.device)),
+          "sgp_reservoir_tc_pack")
+    return out
+
+
+def reservoir_scan_tc(x: torch.Tensor, wimg: torch.Tensor, w_ih: torch.Tensor, bias: torch.Tensor,
+                      alpha: float, activation: str, h_state: torch.Tensor, out: torch.Tensor,
+                      err: torch.Tensor) -> None:
+    """Tensor-core variant of reservoir_scan (same views); `err` is a device int32 flag."""
+    _require_cuda(x, wimg, w_ih, bias, h_state, out, err)
+    _check_view3(x, "x")
+    _check_view3(out, "out")
+    Tc, N, Fin = x.shape
+    H = int(bias.numel())
+    assert out.shape == (Tc, N, H) and h_state.shape == (N, H) and h_state.is_contiguous()
+    a = float(alpha)
+    check(load().sgp_reservoir_scan_tc(_p(x), x.stride(0), x.stride(1), Fin, _p(wimg), _p(w_ih), _p(bias),
+                                       a, float(1.0 - a), ACT_CODES[activation], _p(h_state), _p(out),
+                                       out.stride(0), out.stride(1), Tc, N, H, _p(err), _stream(x.device)),
+          "sgp_reservoir_scan_tc")
+
+
 def spmm(csr: Csr, src: torch.Tensor, dst: torch.Tensor, row_order: Optional[torch.Tensor] = None,
          n_rows: Optional[int] = None, halo: Optional[torch.Tensor] = None, n_split: int = 0) -> None:
     _require_cuda(src, dst, csr.rowptr, halo)

@@ -13,6 +13,7 @@ uniform w_ih, uniform b_ih, uniform w_hh, randperm mask when density < 1, eigval
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -85,6 +86,21 @@ class ReservoirLayer(nn.Module):
             b = torch.zeros(self.hidden_size, device=device)
         return ops.reservoir_pack(w_ih, w_hh), b
 
+    def tensor_core_ok(self) -> bool:
+        """The tcgen05 scan covers H in {128, 256}, Fin <= 8, tanh / relu."""
+        return (self.hidden_size in (128, 256) and self.w_ih.shape[1] <= 8 and
+                self.activation_name in ("tanh", "relu"))
+
+    def device_weights_tc(self, device):
+        """(wimg, w_ih [H, Fin], bias [H]) for the tensor-core scan."""
+        w_ih = self.w_ih.detach().to(device=device, dtype=torch.float32).contiguous()
+        w_hh = self.w_hh.detach().to(device=device, dtype=torch.float32)
+        if self.b_ih is not None:
+            b = self.b_ih.detach().to(device=device, dtype=torch.float32).contiguous()
+        else:
+            b = torch.zeros(self.hidden_size, device=device)
+        return ops.reservoir_tc_pack(w_hh), w_ih, b
+
     def forward(self, x, h):
         """One step for [N, Fin] / [N, H] tensors (a Tc = 1 scan on the device)."""
         dev = _cuda_device_for(x)
@@ -128,26 +144,51 @@ class Reservoir(nn.Module):
             layer.reset_parameters()
 
     # ---- device-side execution ------------------------------------------------------------
-    def device_plan(self, device) -> List[tuple]:
-        """[(wpack, bias, alpha)] per layer, uploaded/packed for `device`."""
-        return [(*layer.device_weights(device), float(layer.alpha)) for layer in self.reservoir_layers]
+    # tensor-core scan: "auto" (node count >= 2048 and the layer qualifies) | "tc" | "cuda"
+    tc_mode = os.environ.get("SGP_B200_RESERVOIR", "auto")
+
+    def device_plan(self, device, num_nodes: Optional[int] = None) -> List[tuple]:
+        """Per layer ("cuda", wpack, bias, alpha) or ("tc", wimg, w_ih, bias, alpha, err_flag),
+        uploaded/packed for `device`."""
+        plan = []
+        for layer in self.reservoir_layers:
+            use_tc = layer.tensor_core_ok() and (
+                self.tc_mode == "tc" or (self.tc_mode == "auto" and (num_nodes or 0) >= 2048))
+            if use_tc:
+                plan.append(("tc", *layer.device_weights_tc(device), float(layer.alpha),
+                             torch.zeros(1, dtype=torch.int32, device=device)))
+            else:
+                plan.append(("cuda", *layer.device_weights(device), float(layer.alpha)))
+        return plan
 
     def scan_chunk(self, plan, x_chunk: torch.Tensor, h_state: torch.Tensor, out: torch.Tensor) -> None:
         """Advance all layers over one chunk.  x_chunk [Tc,N,Fin] (device), h_state [L,N,H] in/out,
         out [Tc,N,>=L*H] view: layer l writes features [l*H,(l+1)*H) and reads layer l-1's block."""
         H = self.hidden_size
         inp = x_chunk
-        for l, (wpack, b, alpha) in enumerate(plan):
+        for l, entry in enumerate(plan):
             blk = out[..., l * H:(l + 1) * H]
-            ops.reservoir_scan(inp, wpack, b, alpha, self.mode, h_state[l], blk)
+            if entry[0] == "tc":
+                _, wimg, w_ih, b, alpha, err = entry
+                ops.reservoir_scan_tc(inp, wimg, w_ih, b, alpha, self.mode, h_state[l], blk, err)
+            else:
+                _, wpack, b, alpha = entry
+                ops.reservoir_scan(inp, wpack, b, alpha, self.mode, h_state[l], blk)
             inp = blk
+
+    @staticmethod
+    def check_plan(plan) -> None:
+        """Raise if a tensor-core scan reported a barrier timeout (synchronises)."""
+        for entry in plan:
+            if entry[0] == "tc" and int(entry[-1].item()) != 0:
+                raise SgpError("sgp_reservoir_scan_tc: internal barrier timed out (results invalid)")
 
     def forward(self, x, h0=None, return_last_state=False):
         """x [b, s, n, f] -> [b, s, n, L*H] on x's device (b*n nodes are scanned together)."""
         B, S, N, Fin = x.size()
         dev = _cuda_device_for(x)
         L, H = len(self.reservoir_layers), self.hidden_size
-        plan = self.device_plan(dev)
+        plan = self.device_plan(dev, B * N)
         # 'b s n f -> s (b n) f'
         xd = x.detach().to(device=dev, dtype=torch.float32).permute(1, 0, 2, 3).reshape(S, B * N, Fin)
         xd = xd.contiguous()
@@ -157,6 +198,7 @@ class Reservoir(nn.Module):
             state = h0.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
         out = torch.empty(S, B * N, L * H, device=dev)
         self.scan_chunk(plan, xd, state, out)
+        self.check_plan(plan)
         # 's (b n) (l f) -> b s n (l f)'
         out = out.view(S, B, N, L * H).permute(1, 0, 2, 3)
         if return_last_state:

@@ -177,7 +177,7 @@ class RowShardedEncoder:
         res, spat = enc.reservoir, enc.sgp_encoder
         T = x_own.shape[0]
         L, H, K, D = res.num_layers, res.hidden_size, spat.receptive_field, enc.output_size
-        plan = res.device_plan(dev)
+        plan = res.device_plan(dev, pl.n_own)
         state = torch.zeros(L, pl.n_own, H, device=dev)
         step = chunk_steps
         n_send = int(self.send_index.numel())

@@ -76,6 +76,50 @@ def test_scan_tiled_kernel_sizes():
         assert_blocks_close(y, ref, 256)
 
 
+def run_scan_tc(x, layer, act, chunk=None):
+    """Drive sgp_reservoir_scan_tc (tcgen05, 3xTF32) for one layer."""
+    x = torch.as_tensor(x, device=DEV)
+    T, N, _ = x.shape
+    H = layer["w_hh"].shape[0]
+    out = torch.empty(T, N, H, device=DEV)
+    state = torch.zeros(N, H, device=DEV)
+    wimg = ops.reservoir_tc_pack(layer["w_hh"].to(DEV))
+    w_ih, b = layer["w_ih"].to(DEV).contiguous(), layer["b_ih"].to(DEV)
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    step = chunk or T
+    for t0 in range(0, T, step):
+        ops.reservoir_scan_tc(x[t0:t0 + step], wimg, w_ih, b, layer["alpha"], act, state, out[t0:t0 + step], err)
+    assert int(err.item()) == 0, "tensor-core scan reported a barrier timeout"
+    return out.cpu().numpy(), state.cpu().numpy()
+
+
+@pytest.mark.parametrize("H,N,Fin,act", [(256, 300, 1, "tanh"), (256, 129, 3, "tanh"), (128, 700, 3, "tanh"),
+                                          (128, 64, 2, "relu"), (256, 1000, 8, "tanh")])
+def test_scan_tensor_core_vs_oracle(H, N, Fin, act):
+    torch.manual_seed(H + N + Fin)
+    layers = O.draw_reservoir(Fin, H, 1, 0.9, 0.9, 0.7)
+    x = np.random.default_rng(N).standard_normal((50, N, Fin)).astype(np.float32)
+    ref = O.reservoir_states(x, layers, act).numpy()
+    y, st = run_scan_tc(x, layers[0], act)
+    assert_blocks_close(y, ref, H)
+    np.testing.assert_array_equal(st, y[-1])
+    part, st2 = run_scan_tc(x, layers[0], act, chunk=7)           # state carried across chunks
+    np.testing.assert_array_equal(part, y)
+    np.testing.assert_array_equal(st2, st)
+
+
+def test_scan_tensor_core_long_recurrence():
+    """1000 steps at H=256 against the float64 oracle: 3xTF32 keeps fp32-level accuracy."""
+    torch.manual_seed(9)
+    layers = O.draw_reservoir(1, 256, 1, 0.9, 0.9, 0.7)
+    x = sensor_signal(1000, 130, seed=4, exogenous=False)
+    ref = O.reservoir_states(x, layers, "tanh", dtype=torch.float64).numpy()
+    y, _ = run_scan_tc(x, layers[0], "tanh")
+    assert_blocks_close(y[-50:], ref[-50:], 256)
+    y32, _ = run_scan(x, layers, "tanh")
+    assert float(np.abs(y - y32).max()) < 2e-5
+
+
 def test_scan_chunked_equals_unchunked_and_carries_state():
     torch.manual_seed(3)
     layers = O.draw_reservoir(3, 128, 2, 0.9, 0.9, 0.7, alpha_decay=True)

@@ -34,7 +34,8 @@ print("nnz", op.csr.nnz, "rbu", None if op.rbu is None else (op.rbu.R, round(op.
 x = torch.from_numpy(sensor_signal(args.tc, N, seed=1, exogenous=Fin == 3)).to(dev)
 torch.manual_seed(2)
 res = sgp_b200.Reservoir(Fin, H, density=0.7)
-plan = res.device_plan(dev)
+plan = res.device_plan(dev, N)
+print('reservoir path:', plan[0][0])
 buf = torch.zeros(args.tc, N, 3 * H, device=dev)
 state = torch.zeros(1, N, H, device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
