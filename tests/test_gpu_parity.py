@@ -99,9 +99,18 @@ def test_scan_tensor_core_vs_oracle(H, N, Fin, act):
     torch.manual_seed(H + N + Fin)
     layers = O.draw_reservoir(Fin, H, 1, 0.9, 0.9, 0.7)
     x = np.random.default_rng(N).standard_normal((50, N, Fin)).astype(np.float32)
-    ref = O.reservoir_states(x, layers, act).numpy()
+    # float64 oracle: independent of the host's fp32 GEMM kernel; on failure say who is off
+    ref = O.reservoir_states(x, layers, act, dtype=torch.float64).numpy()
     y, st = run_scan_tc(x, layers[0], act)
-    assert_blocks_close(y, ref, H)
+    ok, worst = O.blockwise_allclose(y, ref, H)
+    if not ok:
+        ref32 = O.reservoir_states(x, layers, act).numpy()
+        y32, _ = run_scan(x, layers, act)
+        e = np.abs(y - ref)
+        t, n, c = np.unravel_index(int(e.argmax()), e.shape)
+        raise AssertionError(f"worst |err|/tol = {worst:.3g}; max |err| {e.max():.3e} at t={t} node={n} col={c}; "
+                             f"fp32 oracle vs f64 {np.abs(ref32 - ref).max():.3e}; CUDA-core scan vs f64 "
+                             f"{np.abs(y32 - ref).max():.3e}; errors by step {np.round(e.max(axis=(1, 2))[:12], 7)}")
     np.testing.assert_array_equal(st, y[-1])
     part, st2 = run_scan_tc(x, layers[0], act, chunk=7)           # state carried across chunks
     np.testing.assert_array_equal(part, y)
