@@ -10,10 +10,10 @@
 // gather traffic drops another 2x (U/R = 5.4 at R = 64 against 11.3 at R = 16 on the 100-NN
 // graph), which is what lets the hop approach the HBM roofline.
 //
-//   * A = X^T chunk (32 gathered rows x 128 features): M-major ("MN-major") tf32 operand in the
-//     SWIZZLE_128B_BASE32B canonical layout — the only MN-major layout tcgen05 takes for 32-bit
-//     types.  Every lane cp.async's 16 bytes of a gathered row straight to its swizzled place, so
-//     the gather needs no registers and no transposition.
+//   * A = X^T chunk (32 gathered rows x 128 features), fed to the MMA from TMEM (TS mode: lane =
+//     feature, column = gathered row).  The gather is cp.async (16 bytes per lane, a warp per 512-byte
+//     row piece) into a row-major ring stage; the copies signal the stage's mbarrier themselves
+//     (cp.async.mbarrier.arrive.noinc), so the whole 8-stage ring stays in flight.
 //   * B = slab chunk (64 rows x 32 columns), K-major SWIZZLE_128B, pre-swizzled at operator build
 //     time, streamed linearly with cp.async and reused for 8 accumulators (4 time steps x 2 feature
 //     chunks at F = 256) so that its HBM traffic is amortised.
@@ -45,13 +45,17 @@ constexpr int kTcR = 64;            // rows per group  (MMA N)
 constexpr int kTcKC = 32;           // union columns per chunk
 constexpr int kTcAcc = 4;           // accumulators per CTA (time steps x feature chunks)
 constexpr int kTcABufs = 4;         // A (hi | lo) tiles resident in TMEM
-constexpr int kTcSplitGroups = 2;   // split groups alternate items
+#ifndef SGP_TC_PRODUCER_WARPS
+#define SGP_TC_PRODUCER_WARPS 4
+#endif
+#ifndef SGP_TC_SPLIT_GROUPS
+#define SGP_TC_SPLIT_GROUPS 4
+#endif
+constexpr int kTcSplitGroups = SGP_TC_SPLIT_GROUPS;   // split groups take items round-robin (group = accumulator index at 4)
 constexpr int kTcSplitWarps = 4 * kTcSplitGroups;   // lo-pass + epilogue warps (warp & 3 = TMEM lane quarter)
-constexpr int kTcProducerWarps = 4; // gather (cp.async) warps
-constexpr int kTcThreads = (kTcSplitWarps + kTcProducerWarps + 1) * 32;   // + 1 MMA-issuing warp
-constexpr int kTcLag = 5;           // cp.async groups a producer thread keeps in flight
+constexpr int kTcIssuers = 2;       // MMA-issuing warps (one elected thread each)
 constexpr int kTcStages = 8;        // gathered-row ring in shared memory
-constexpr int kTcStageBytes = kTcKC * 128 * 4;      // 16 KB: 32 rows x 128 features
+constexpr int kTcStageBytes = kTcKC * 128 * 4;      // 16 KB: 32 rows x 128 features, row-major
 constexpr int kTcBBytes = 2 * kTcR * kTcKC * 4;     // 16 KB: hi + lo image of one chunk
 constexpr int kTcBBufs = 3;         // slab-image buffers (3: a producer may only wait on MMAs >= 3 chunks old,
                                     // anything newer can depend on items it has not signalled yet)
@@ -119,6 +123,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// producer side of a byte-counted barrier: one arrival + the bytes the bulk copies will deliver
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (no tensor map), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 
 // Bounded warp-wide wait (all 32 lanes poll the same word: one broadcast shared-memory access per
 // try).  A barrier that never completes raises the error flag and the CTA-wide abort flag (so that
@@ -140,13 +154,11 @@ __device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volati
     return false;
 }
 
-// byte offset of (gathered row k in [0,32), 16-byte piece q in [0,32)) inside an A stage:
-// atoms [k/4][q/8] of 4 rows x 128 B; the 32-byte chunk index inside a row is XORed with k%4
-__device__ __forceinline__ int a_stage_offset(int k, int q) {
-    const int r = k & 3, ch = q & 7;
-    return ((k >> 2) * 4 + (q >> 3)) * 512 + r * 128 + ((((ch >> 1) ^ r) << 5) | ((ch & 1) << 4));
-}
-
+#define SGP_TMEM_ST16(addr, arr)                                                                   \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+                 :: "r"(addr), "r"(arr[0]), "r"(arr[1]), "r"(arr[2]), "r"(arr[3]), "r"(arr[4]), "r"(arr[5]),  \
+                    "r"(arr[6]), "r"(arr[7]), "r"(arr[8]), "r"(arr[9]), "r"(arr[10]), "r"(arr[11]),            \
+                    "r"(arr[12]), "r"(arr[13]), "r"(arr[14]), "r"(arr[15]) : "memory")
 #define SGP_TMEM_ST32(addr, arr)                                                                   \
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,"  \
                  "%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"       \
@@ -171,8 +183,8 @@ __device__ __forceinline__ int a_stage_offset(int k, int q) {
 // memory (thread = feature = TMEM lane, 32 k values), form hi / lo in registers and tcgen05.st
 // them; the 12 MMAs of an item then fetch only the 2 KB slab operand from shared memory each, so
 // shared-memory bandwidth (the limit of the all-in-smem version: 120 KB per item) drops to 56 KB.
-template <int NFC, bool HALO>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int NFC, bool HALO, int kTcProducerWarps>
+__global__ void __launch_bounds__((kTcSplitWarps + kTcProducerWarps + kTcIssuers) * 32, 1)
 spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ grp_rows,
                    const int32_t* __restrict__ cols, const float* __restrict__ bimg,
                    int n_groups, int n_work,
@@ -183,19 +195,26 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
     constexpr int TB = kTcAcc / NFC;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-window address
-    __shared__ uint64_t full[kTcStages], empty[kTcStages], ready[kTcABufs], afree[kTcABufs], bfree[kTcBBufs];
+    __shared__ uint64_t full[kTcStages], empty[kTcStages], ready[kTcABufs], afree[kTcABufs], bfree[kTcBBufs], bfull[kTcBBufs];
     __shared__ uint64_t done, accfree[kTcAcc];
     __shared__ uint32_t tmem_base_s;
     __shared__ volatile int abort_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // optional per-item timestamps of CTA 7 (tools/trace_tc.py); trace == nullptr in production
+    // (compiled in only with -DSGP_TC_TRACE: even predicated-off, the stamps cost a lone warp ~75 cycles per item)
+#ifdef SGP_TC_TRACE
     const bool tr = trace && blockIdx.x == 7;
 #define SGP_TRACE(role, i) do { if (tr && lane == 0 && (i) < 512) trace[(role) * 512 + (i)] = clock64(); } while (0)
+#define SGP_TRACE1(role, i) do { if (tr) trace[(role) * 512 + min((i), 511)] = clock64(); } while (0)
+#else
+#define SGP_TRACE(role, i) do { } while (0)
+#define SGP_TRACE1(role, i) do { } while (0)
+#endif
 
     if (tid == 0) {
         abort_s = 0;
         for (int s = 0; s < kTcStages; ++s) {
-            mbar_init(&full[s], kTcProducerWarps);
+            mbar_init(&full[s], 32);             // the 32 lanes' cp.async arrivals
             mbar_init(&empty[s], 4);
         }
         for (int b = 0; b < kTcABufs; ++b) {
@@ -203,8 +222,11 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             mbar_init(&afree[b], 1);
             mbar_init(&accfree[b], 4);
         }
-        for (int b = 0; b < kTcBBufs; ++b) mbar_init(&bfree[b], 1);
-        mbar_init(&done, 1);
+        for (int b = 0; b < kTcBBufs; ++b) {
+            mbar_init(&bfree[b], kTcIssuers);
+            mbar_init(&bfull[b], 1);           // producer 0's arrive.expect_tx; the bulk copy completes the bytes
+        }
+        mbar_init(&done, kTcIssuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -225,25 +247,24 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
     // items with at least one chunk.  The producers simply run on into the next work item while
     // the split warps drain the accumulators of the previous one.
     if (warp >= kTcSplitWarps && warp < kTcSplitWarps + kTcProducerWarps) {
-        // ================= producers: item `it` -> ring stage it % 8 ===========================
-        const int pw = warp - kTcSplitWarps, ptid = tid - kTcSplitWarps * 32;
-        constexpr int kRowsPerWarp = kTcKC / kTcProducerWarps;       // 8 gathered rows per warp per item
-        uint32_t dst_off[kRowsPerWarp];                              // swizzled byte offset of my 16 B
-#pragma unroll
-        for (int j = 0; j < kRowsPerWarp; ++j)
-            dst_off[j] = smem_base + a_stage_offset(pw + j * kTcProducerWarps, lane);
-        uint32_t off1[kRowsPerWarp];      // byte offset of each of my rows inside its source
-        bool in2[kRowsPerWarp];
+        // ================= producers: warp p gathers the items with accumulator index a = p ======
+        // One item = 32 source rows x 512 bytes: a cp.async per row, the 32 lanes covering its 128
+        // features, landing row-major in ring stage it % 8.  Completion is signalled by the copies
+        // themselves (cp.async.mbarrier.arrive.noinc on full[s]), so a producer waits for nothing
+        // but a free stage and the ring stays full; with commit/wait_group signalling only ~5
+        // items were in flight at 4300 cycles of loaded gather latency.  Whole items per warp (not
+        // rows of every item) because a lone warp issues ~1 instruction per 5 cycles: the per-item
+        // overhead (waits, barrier addresses) is paid once per chunk and warp, not four times.
+        // (One 512-byte TMA bulk copy per row was tried: ~75 cycles per request, 2400 per item.)
+        // The chunk's slab images ride on item a = 0's barrier as one 16 KB TMA bulk copy.
+        static_assert(kTcProducerWarps == kTcAcc, "one producer warp per accumulator index");
+        const int pw = warp - kTcSplitWarps;
         const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-        int it = 0, bi = 0, bph = 0;
+        const uint32_t full0 = smem_u32(&full[0]), dst0 = smem_base + lane * 16;
+        int it = pw, bi = 0, bph = 0;
         bool ok = true;
-        // source-row ids of the NEXT chunk are fetched while the current chunk is being issued
-        int coln[kRowsPerWarp];
-        auto fetch_cols = [&](long long chunk) {
-#pragma unroll
-            for (int j = 0; j < kRowsPerWarp; ++j)
-                coln[j] = __ldg(cols + (size_t)chunk * kTcKC + pw + j * kTcProducerWarps);
-        };
+        // lane j holds the source-row id j of the NEXT chunk, fetched while the current one is issued
+        int coln = 0;
         auto first_chunk_of = [&](int w) -> long long {        // first chunk of the next non-empty work item
             for (; w < n_work; w += gridDim.x) {
                 const int g2 = w % n_groups;
@@ -253,77 +274,63 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         };
         {
             const long long f = first_chunk_of(blockIdx.x);
-            if (f >= 0) fetch_cols(f);
+            if (f >= 0) coln = __ldg(cols + (size_t)f * kTcKC + lane);
         }
         for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
             const int g = w % n_groups, t_begin = (w / n_groups) * TB;
             const int c_beg = chunk_ptr[g], n_chunks = chunk_ptr[g + 1] - c_beg;
-            auto base_of = [&](const float* sbase, int64_t ts, int a) -> const char* {
-                const int t = min(t_begin + a / NFC, Tc - 1);      // out-of-range steps are clamped
-                return reinterpret_cast<const char*>(sbase + (size_t)t * ts + (a % NFC) * 128 + lane * 4);
-            };
-            for (int c = 0; c < n_chunks && ok; ++c) {
-#pragma unroll
-                for (int j = 0; j < kRowsPerWarp; ++j) {
-                    const int col = coln[j];
-                    in2[j] = HALO && col >= n_split;
-                    off1[j] = in2[j] ? (uint32_t)(col - n_split) * s2_nb : (uint32_t)col * s_nb;
-                }
+            const int t = min(t_begin + pw / NFC, Tc - 1);             // out-of-range steps are clamped
+            const char* b1 = reinterpret_cast<const char*>(src + (size_t)t * s_ts + (pw % NFC) * 128) + lane * 16;
+            const char* b2 = HALO ? reinterpret_cast<const char*>(src2 + (size_t)t * s2_ts + (pw % NFC) * 128) + lane * 16 : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < n_chunks && ok; ++c, it += kTcAcc) {
+                const int col = coln;
+                const bool in2 = HALO && col >= n_split;
+                // byte offset of row `lane` inside its source (bit 31: the row lives in src2)
+                const uint32_t mine = in2 ? (((uint32_t)(col - n_split) * s2_nb) | 0x80000000u) : (uint32_t)col * s_nb;
                 {
                     const long long nxt = (c + 1 < n_chunks) ? (long long)(c_beg + c + 1) : first_chunk_of(w + gridDim.x);
-                    if (nxt >= 0) fetch_cols(nxt);
+                    if (nxt >= 0) coln = __ldg(cols + (size_t)nxt * kTcKC + lane);
                 }
-#pragma unroll 1
-                for (int a = 0; a < kTcAcc; ++a, ++it) {
-                    const int s = it & (kTcStages - 1);
-                    if (it >= kTcStages && !warp_wait(&empty[s], ((it >> 3) + 1) & 1, &abort_s, err, lane)) { ok = false; break; }
-                    if (pw == 0) SGP_TRACE(0, it);
-                    const char* b1 = base_of(src, s_ts, a);
-                    const char* b2 = HALO ? base_of(src2, s2_ts, a) : nullptr;
+                const int s = it & (kTcStages - 1);
+                if (it >= kTcStages && !warp_wait(&empty[s], ((it >> 3) + 1) & 1, &abort_s, err, lane)) { ok = false; break; }
+                if (pw == 0 && bph > 0 && !warp_wait(&bfree[bi], (bph - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
+                SGP_TRACE(0, it);
+                const uint32_t dst = dst0 + s * kTcStageBytes, fbar = full0 + s * 8;
 #pragma unroll
-                    for (int j = 0; j < kRowsPerWarp; ++j) {
-                        const char* p = (HALO && in2[j]) ? b2 + off1[j] : b1 + off1[j];
-                        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n"
-                                     :: "r"(dst_off[j] + s * kTcStageBytes), "l"(p), "l"(pol_keep));
-                    }
-                    if (a == 0) {   // the chunk's slab images (hi | lo), reused by its 4 items
-                        if (bph > 0 && !warp_wait(&bfree[bi], (bph - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
-                        const float* bs = bimg + (size_t)(c_beg + c) * (kTcBBytes / 4);
-                        const uint32_t bd = smem_base + kBOff + bi * kTcBBytes;
-                        if (++bi == kTcBBufs) { bi = 0; ++bph; }
-#pragma unroll
-                        for (int j = 0; j < kTcBBytes / 16 / (kTcProducerWarps * 32); ++j)
-                            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n"
-                                         :: "r"(bd + (j * kTcProducerWarps * 32 + ptid) * 16),
-                                            "l"(bs + (j * kTcProducerWarps * 32 + ptid) * 4), "l"(pol_stream));
-                    }
-                    cp_async_commit();
-                    if (it >= kTcLag) {          // signal item it - kTcLag (kTcLag groups stay in flight)
-                        cp_async_wait<kTcLag>();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&full[(it - kTcLag) & (kTcStages - 1)]);
-                        if (pw == 0) SGP_TRACE(1, it - kTcLag);
-                    }
+                for (int j = 0; j < kTcKC; ++j) {
+                    const uint32_t off = __shfl_sync(0xffffffffu, mine, j);
+                    const char* p = (HALO && (off >> 31)) ? b2 + (off & 0x7fffffffu) : b1 + off;
+                    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n"
+                                 :: "r"(dst + j * 512), "l"(p), "l"(pol_keep));
                 }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(fbar) : "memory");
+                if (pw == 0 && lane == 0) {   // the chunk's slab images (hi | lo), reused by its 4 items: bfull[bi]
+                    const uint32_t bbar = smem_u32(&bfull[bi]);
+                    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
+                                 :: "r"(bbar), "r"(kTcBBytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                                 :: "r"(smem_base + kBOff + bi * kTcBBytes), "l"(bimg + (size_t)(c_beg + c) * (kTcBBytes / 4)),
+                                    "r"(kTcBBytes), "r"(bbar), "l"(pol_stream) : "memory");
+                }
+                if (++bi == kTcBBufs) { bi = 0; ++bph; }
+                __syncwarp();
             }
         }
-        // drain: signal the last kTcLag items
-        cp_async_wait<0>();
-        __syncwarp();
-        if (ok && lane == 0)
-            for (int j = max(it - kTcLag, 0); j < it; ++j) mbar_arrive(&full[j & (kTcStages - 1)]);
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp < kTcSplitWarps) {
         // ================= split warps: stage (smem) -> A hi | lo tiles (TMEM); epilogue =======
         // two groups of 4 warps; group G takes the items / accumulators with (a & 1) == G
         const int grp = warp >> 2, m = tid & 127;                  // m = feature = TMEM lane
         const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
-        const int q = m >> 2, e = m & 3;                           // 16-byte piece / element of feature m
-        const uint64_t pol_stream = l2_policy_evict_first();
         int it0 = 0, cc = 0, wn = 0;                               // items, chunks, non-empty work items so far
         bool ok = true;
         for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
             const int g = w % n_groups, t_begin = (w / n_groups) * TB;
             const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
+            // destination rows of the group (lane j holds rows j and 32 + j), for the epilogue
+            const int my_row0 = __ldg(grp_rows + (size_t)g * kTcR + lane);
+            const int my_row1 = __ldg(grp_rows + (size_t)g * kTcR + 32 + lane);
             for (int c = 0; c < n_chunks && ok; ++c, ++cc, it0 += kTcAcc) {
 #pragma unroll 1
                 for (int a = grp; a < kTcAcc; a += kTcSplitGroups) {
@@ -332,20 +339,21 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                     if ((warp & 3) == 0) SGP_TRACE(2, it);
                     if (cc > 0 && !warp_wait(&afree[a], (cc - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
                     if ((warp & 3) == 0) SGP_TRACE(3, it);
-                    const uint32_t rs = smem_base + s * kTcStageBytes + (q >> 3) * 512 + e * 4;
-                    uint32_t hv[kTcKC], lv[kTcKC];
-#pragma unroll
-                    for (int k = 0; k < kTcKC; ++k) {
-                        const int r = k & 3, ch = q & 7;
-                        const uint32_t off = (k >> 2) * 2048 + r * 128 + ((((ch >> 1) ^ r) << 5) | ((ch & 1) << 4));
-                        float x;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(rs + off));
-                        hv[k] = __float_as_uint(x);        // the tensor core ignores the low 13 mantissa bits
-                        lv[k] = __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
-                    }
+                    const uint32_t rs = smem_base + s * kTcStageBytes + m * 4;     // row-major stage: [k][feature]
                     const uint32_t ta = lane_addr + kTcAOff + a * 64;
-                    SGP_TMEM_ST32(ta, hv);
-                    SGP_TMEM_ST32(ta + 32, lv);
+#pragma unroll
+                    for (int k0 = 0; k0 < kTcKC; k0 += 16) {       // two halves: 32 live registers, not 64
+                        uint32_t hv[16], lv[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            float x;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(rs + (k0 + k) * 512));
+                            hv[k] = __float_as_uint(x);    // the tensor core ignores the low 13 mantissa bits
+                            lv[k] = __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+                        }
+                        SGP_TMEM_ST16(ta + k0, hv);
+                        SGP_TMEM_ST16(ta + 32 + k0, lv);
+                    }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
@@ -354,6 +362,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                         mbar_arrive(&empty[s]);
                     }
                     if ((warp & 3) == 0) SGP_TRACE(4, it);
+                    SGP_TRACE(8 + (warp & 3), it);
                 }
             }
             if (!ok) break;
@@ -362,10 +371,15 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                 if (!warp_wait(&done, wn & 1, &abort_s, err, lane)) { ok = false; break; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
+            // Kept lean on purpose: the drain is exposed (the next work item's MMAs need the
+            // accumulators), and its first version — a shuffle, a 64-bit multiply and a branch per
+            // row, ~15 dependent instructions — took 9k cycles per work item (38% of the hop).
+            const uint32_t d_nb = (uint32_t)d_ns * 4u;           // row stride in bytes (host checks < 2^32)
 #pragma unroll 1
             for (int a = grp; a < kTcAcc; a += kTcSplitGroups) {
                 const int t = t_begin + a / NFC;
-                float* dp = dst + (size_t)min(t, Tc - 1) * d_ts + (a % NFC) * 128 + (warp & 3) * 32 + lane;
+                const bool t_ok = t < Tc;
+                const char* dp = reinterpret_cast<const char*>(dst + (size_t)min(t, Tc - 1) * d_ts + (a % NFC) * 128 + (warp & 3) * 32 + lane);
 #pragma unroll
                 for (int j = 0; j < kTcR; j += 16) {
                     uint32_t v[16];
@@ -376,18 +390,20 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                                        "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
                                        "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                                      : "r"(lane_addr + a * kTcR + j));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     } else {
 #pragma unroll
                         for (int e2 = 0; e2 < 16; ++e2) v[e2] = 0u;      // group without entries: zero rows
                     }
-                    if (t < Tc) {
+                    int rows[16];
 #pragma unroll
-                        for (int e2 = 0; e2 < 16; ++e2) {
-                            const int row = __ldg(grp_rows + (size_t)g * kTcR + j + e2);
-                            if (row >= 0)
-                                asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(dp + (size_t)row * d_ns), "r"(v[e2]), "l"(pol_stream) : "memory");
-                        }
+                    for (int e2 = 0; e2 < 16; ++e2)
+                        rows[e2] = __shfl_sync(0xffffffffu, (j < 32) ? my_row0 : my_row1, (j & 31) + e2);
+                    if (n_chunks > 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e2 = 0; e2 < 16; ++e2) {
+                        if (t_ok && rows[e2] >= 0)
+                            asm volatile("st.global.cs.b32 [%0], %1;"      // streaming (evict-first): written once, read by the next hop's launch
+                                         :: "l"(dp + (uint64_t)(uint32_t)rows[e2] * d_nb), "r"(v[e2]) : "memory");
                     }
                 }
                 if (n_chunks > 0) {       // accumulator a may be overwritten by the next work item
@@ -399,57 +415,87 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             if (n_chunks > 0) ++wn;
         }
     } else {
-        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues ===
+        // ================= MMA issuers: two warps, ONE elected thread each runs the whole loop ===
+        // issuer q takes the items with (a & 1) == q: a lone thread needs ~500 cycles of
+        // instruction latency per item, the tensor pipe 384
         // kind::tf32, fp32 accumulate, A from TMEM (lane = feature, column = k), B K-major smem,
-        // N = 64, M = 128
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
-                                   ((uint32_t)(kTcR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t b_hi32 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SW128
-        constexpr uint32_t b_lo32 = (16u >> 4) << 16;                          // LBO
-        auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
-        auto mma_ts = [](uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc_, uint32_t acc) {
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
-                         :: "r"(d), "r"(a_tmem), "l"(db), "r"(idesc_), "r"(acc) : "memory");
-        };
-        const uint32_t bb0 = b_lo32 | ((smem_base + kBOff) >> 4);
-        int bi = 0, cc = 0, wn = 0, itn = 0;
-        bool ok = true;
-        for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
-            const int g = w % n_groups;
-            const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
-            for (int c = 0; c < n_chunks && ok; ++c, ++cc) {
-                const uint32_t bh = bb0 + bi * (kTcBBytes >> 4), bl = bh + (kTcBBytes >> 5);
+        // N = 64, M = 128.  The loop is kept minimal on purpose: a lone warp issues dependent
+        // instructions ~5 cycles apart, and 12 MMAs of 32 cycles leave 384 cycles per item — the
+        // first version (warp-wide waits, per-item elect, addresses recomputed per barrier: ~85
+        // instructions per item) ran the tensor pipe at half rate (profiles/r1_trace_tc.txt).
+        // Barrier addresses and descriptors are computed once; the four items of a chunk are
+        // unrolled so that every MMA operand is a constant offset from a handful of registers.
+        if (elect_one()) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) |
+                                       ((uint32_t)(kTcR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t b_hi32 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SW128
+            constexpr uint32_t b_lo32 = (16u >> 4) << 16;                          // LBO
+            const uint32_t ready0 = smem_u32(&ready[0]), afree0 = smem_u32(&afree[0]), bfree0 = smem_u32(&bfree[0]);
+            const uint32_t accfree0 = smem_u32(&accfree[0]), done_a = smem_u32(&done), bfull0 = smem_u32(&bfull[0]);
+            // single-thread bounded wait
+            auto wait1 = [&](uint32_t bar, uint32_t parity) -> bool {
+                uint32_t ok1 = 0;
 #pragma unroll 1
-                for (int a = 0; a < kTcAcc; ++a, ++itn) {
-                    if (!warp_wait(&ready[a], cc & 1, &abort_s, err, lane)) { ok = false; break; }
-                    // first MMA into accumulator a of this work item: the previous one must be drained
-                    if (c == 0 && wn > 0 && !warp_wait(&accfree[a], (wn - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
-                    SGP_TRACE(5, itn);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (elect_one()) {
+                for (int spin = 0; spin < (1 << 24); ++spin) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok1) : "r"(bar), "r"(parity) : "memory");
+                    if (ok1) return true;
+                    if ((spin & 63) == 63 && abort_s) return false;
+                }
+                abort_s = 1;
+                atomicExch(err, 1);
+                return false;
+            };
+            auto commit1 = [](uint32_t bar) {
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+            };
+            auto mma_ts = [](uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t acc) {
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %3, 0;\n\tmov.b64 db, {%2, %5};\n\t"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}\n"
+                             :: "r"(d), "r"(a_tmem), "r"(b_lo), "r"(acc), "r"(idesc), "r"(b_hi32) : "memory");
+            };
+            const uint32_t bb0 = b_lo32 | ((smem_base + kBOff) >> 4);
+            const int q = warp - (kTcSplitWarps + kTcProducerWarps);
+            int bi = 0, bph = 0, cc = 0, wn = 0, itn = q;
+            bool ok = true;
+            for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
+                const int g = w % n_groups;
+                const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
+#pragma unroll 1
+                for (int c = 0; c < n_chunks && ok; ++c, ++cc) {
+                    const uint32_t bh = bb0 + bi * (kTcBBytes >> 4), bl = bh + (kTcBBytes >> 5);
+                    const uint32_t par = cc & 1;
+                    if (!wait1(bfull0 + bi * 8, bph & 1)) { ok = false; break; }      // the chunk's slab images have landed
+#pragma unroll
+                    for (int a2 = 0; a2 < kTcAcc; a2 += kTcIssuers, itn += kTcIssuers) {
+                        const int a = a2 + q;
+                        SGP_TRACE1(7, itn);
+                        if (!wait1(ready0 + a * 8, par)) { ok = false; break; }
+                        // first MMA into accumulator a of this work item: the previous one must be drained
+                        if (c == 0 && wn > 0 && !wait1(accfree0 + a * 8, (wn - 1) & 1)) { ok = false; break; }
+                        SGP_TRACE1(5, itn);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t ah = tmem_d + kTcAOff + a * 64, al = ah + 32;
                         const uint32_t d = tmem_d + a * kTcR;
 #pragma unroll
                         for (int ks = 0; ks < kTcKC / 8; ++ks) {
-                            const uint64_t dbh = desc(bh + ks * 2, b_hi32), dbl = desc(bl + ks * 2, b_hi32);
-                            mma_ts(d, ah + ks * 8, dbh, idesc, (c | ks) ? 1u : 0u);
-                            mma_ts(d, al + ks * 8, dbh, idesc, 1u);
-                            mma_ts(d, ah + ks * 8, dbl, idesc, 1u);
+                            mma_ts(d, ah + ks * 8, bh + ks * 2, (c | ks) ? 1u : 0u);
+                            mma_ts(d, al + ks * 8, bh + ks * 2, 1u);
+                            mma_ts(d, ah + ks * 8, bl + ks * 2, 1u);
                         }
-                        umma_commit(&afree[a]);                          // A tile a may be rewritten
-                        if (a == kTcAcc - 1) {
-                            umma_commit(&bfree[bi]);                      // slab buffer may be refilled
-                            if (c == n_chunks - 1) umma_commit(&done);    // accumulators complete
+                        commit1(afree0 + a * 8);                          // A tile a may be rewritten
+                        if (a2 == kTcAcc - kTcIssuers) {                  // this issuer's last item of the chunk
+                            commit1(bfree0 + bi * 8);                     // slab buffer may be refilled
+                            if (c == n_chunks - 1) commit1(done_a);       // accumulators complete
                         }
+                        SGP_TRACE1(6, itn);
                     }
-                    __syncwarp();
-                    SGP_TRACE(6, itn);
+                    if (++bi == kTcBBufs) { bi = 0; ++bph; }
                 }
-                if (++bi == kTcBBufs) bi = 0;
+                if (n_chunks > 0) ++wn;
             }
-            if (n_chunks > 0) ++wn;
         }
+        __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -483,17 +529,22 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
     // gathered-row byte offsets are 32-bit inside the kernel
     SGP_REQUIRE(src_n_stride > 0 && src_n_stride * 4 < (1ll << 31) / 64 && (!src2 || (src2_n_stride > 0 && src2_n_stride * 4 < (1ll << 31) / 64)),
                 SGP_EUNSUPPORTED, "sgp_spmm_rbu_tc: row stride too large");
+    SGP_REQUIRE(dst_n_stride > 0 && dst_n_stride * 4 < (1ll << 32), SGP_EUNSUPPORTED, "sgp_spmm_rbu_tc: dst row stride too large");
     const uint32_t s_nb = (uint32_t)(src_n_stride * 4), s2_nb = (uint32_t)(src2_n_stride * 4);
     const int n_work = n_groups * ny;
     const int grid = n_work < kNumSMs ? n_work : kNumSMs;        // persistent: one CTA per SM
     long long* trace_ptr = getenv("SGP_B200_TC_TRACE") ? (long long*)strtoull(getenv("SGP_B200_TC_TRACE"), nullptr, 10) : nullptr;
-#define SGP_TC(NFC_, HALO_)                                                                            \
+#define SGP_TC3(NFC_, HALO_, PW_)                                                                      \
     do {                                                                                               \
-        SGP_CUDA(cudaFuncSetAttribute(spmm_rbu_tc_kernel<NFC_, HALO_>,                                 \
+        SGP_CUDA(cudaFuncSetAttribute(spmm_rbu_tc_kernel<NFC_, HALO_, PW_>,                            \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));     \
-        spmm_rbu_tc_kernel<NFC_, HALO_><<<grid, kTcThreads, kTcSmem, as_stream(stream)>>>(             \
+        spmm_rbu_tc_kernel<NFC_, HALO_, PW_><<<grid, (kTcSplitWarps + PW_ + kTcIssuers) * 32, kTcSmem, as_stream(stream)>>>( \
             chunk_ptr, grp_rows, cols, bimg, n_groups, n_work, src, src_t_stride, s_nb, src2,          \
             src2_t_stride, s2_nb, n_split, dst, dst_t_stride, dst_n_stride, Tc, err_flag, trace_ptr);  \
+    } while (0)
+#define SGP_TC(NFC_, HALO_)                                                                            \
+    do {                                                                                               \
+        SGP_TC3(NFC_, HALO_, SGP_TC_PRODUCER_WARPS);                                                                    \
     } while (0)
     if (src2) {
         if (nfc == 1) SGP_TC(1, true); else if (nfc == 2) SGP_TC(2, true); else SGP_TC(4, true);
@@ -501,6 +552,7 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
         if (nfc == 1) SGP_TC(1, false); else if (nfc == 2) SGP_TC(2, false); else SGP_TC(4, false);
     }
 #undef SGP_TC
+#undef SGP_TC3
     SGP_LAUNCH_CHECK("spmm_rbu_tc");
     return SGP_OK;
 }

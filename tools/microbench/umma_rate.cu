@@ -12,6 +12,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+template <int nacc>
 __global__ void __launch_bounds__(128, 1) rate(int N, int amajor, int iters, long long* out, int distinct, int ts) {
     extern __shared__ __align__(1024) uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -26,15 +27,15 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int amajor, int iters, lon
         const uint32_t a0 = smem_u32(smem), b0 = a0 + 8 * 16384;
         long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
-#pragma unroll
             const uint32_t a = a0 + (distinct ? (it & 7) * 16384 : 0), b = b0 + (distinct ? (it & 1) * 32768 : 0);
+#pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t da = amajor ? make_desc(a + ks * 4096, 512, 2048, 1) : make_desc(a + ks * 32, 16, 1024, 2);
                 const uint64_t db = make_desc(b + ks * 32, 16, 1024, 2);
                 if (ts) {
                     const uint32_t idts = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
-                                 :: "r"(tb), "r"(tb + 256 + (distinct ? (it & 3) * 64 : 0) + ks * 8), "l"(db), "r"(idts), "r"(1u) : "memory");
+                                 :: "r"(tb + (ks % nacc) * 64), "r"(tb + 256 + (distinct ? (it & 3) * 64 : 0) + ks * 8), "l"(db), "r"(idts), "r"(1u) : "memory");
                 } else
                 mma(tb, da, db, idesc, 1u);
             }
@@ -52,16 +53,21 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int amajor, int iters, lon
 }
 int main() {
     long long* d; cudaMalloc(&d, 32); long long h[3];
-    cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    for (int ts = 0; ts < 2; ++ts)
+    cudaFuncSetAttribute(rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);cudaFuncSetAttribute(rate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);cudaFuncSetAttribute(rate<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int nacc : {1, 2, 4})
+    for (int ts = 1; ts < 2; ++ts)
     for (int distinct = 1; distinct < 2; ++distinct)
     for (int amajor = 1; amajor < 2; ++amajor)
-        for (int N : {64, 128, 256})
+        for (int N : {64, 128})
             for (int rep = 0; rep < 2; ++rep) {
                 const int iters = 500;
-                rate<<<1, 128, 198 * 1024>>>(N, amajor, iters, d, distinct, ts);
+                if (N * nacc > 256) continue;
+                if (nacc == 1) rate<1><<<1, 128, 198 * 1024>>>(N, amajor, iters, d, distinct, ts);
+                else if (nacc == 2) rate<2><<<1, 128, 198 * 1024>>>(N, amajor, iters, d, distinct, ts);
+                else rate<4><<<1, 128, 198 * 1024>>>(N, amajor, iters, d, distinct, ts);
                 cudaError_t e = cudaDeviceSynchronize();
                 cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
+                if (rep) printf("nacc=%d ", nacc);
                 if (rep) printf("ts=%d distinct=%d A %s-major N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (done=%lld, %s)  -> %.0f MAC/clk\n", ts, distinct, amajor ? "M" : "K", N,
                        (double)h[0] / (iters * 4), (double)h[1] / (iters * 4), h[2], cudaGetErrorString(e), 128.0 * N * 8 / ((double)h[1] / (iters * 4)));
             }
