@@ -7,8 +7,8 @@
 //      that run concurrently touch a compact part of the source panel, which stays L2-resident);
 //   2. walking that order, every still-unassigned row seeds a group and pulls in its R-1
 //      still-unassigned neighbours with the largest operator weight (on kNN / kernel graphs:
-//      the nearest ones), which are the rows most likely to share its neighbourhood;
-//   3. rows left without enough free neighbours are chunked R at a time in BFS order.
+//      the nearest ones), which are the rows most likely to share its neighbourhood; a seed with
+//      too few free neighbours continues breadth-first over the group's own members.
 #include <algorithm>
 #include <vector>
 
@@ -43,47 +43,51 @@ extern "C" int sgp_group_rows(const int32_t* rowptr, const int32_t* col, const f
         }
     }
 
-    // 2. greedy grouping
+    // 2. greedy grouping.  Every group is a compact blob: the seed's free neighbours by weight,
+    //    then — when the seed sits at the edge of what is already grouped and has too few — the
+    //    free neighbours of the members chosen so far (breadth-first over the blob), and only when
+    //    nothing free is reachable any more the next free row in BFS order.  (Deferring such seeds
+    //    and chunking them at the end left 3% of the rows in ~45 groups of scattered "holes" whose
+    //    column unions were 10x the median: 20% of all gathers and MMAs.)
     std::vector<uint8_t> taken(N, 0);
-    std::vector<int32_t> late;
     std::vector<std::pair<float, int32_t>> cand;
+    size_t next_free = 0;             // scan position in `order` for the jump fallback
     int32_t g = 0;
     for (int32_t i : order) {
         if (taken[i]) continue;
+        int32_t* out = grp_rows + (size_t)g * R;
+        out[0] = i;
+        taken[i] = 1;
+        int32_t filled = 1;
         cand.clear();
         for (int32_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
             const int32_t j = col[e];
             if (j != i && j < N && !taken[j]) cand.emplace_back(-val[e], j);
         }
         std::sort(cand.begin(), cand.end());
-        if ((int32_t)cand.size() < R - 1) { late.push_back(i); continue; }
-        int32_t* out = grp_rows + (size_t)g * R;
-        out[0] = i;
-        taken[i] = 1;
-        int32_t filled = 1;
         for (size_t k = 0; k < cand.size() && filled < R; ++k) {
             const int32_t j = cand[k].second;
             if (taken[j]) continue;   // duplicate edge to the same neighbour
             out[filled++] = j;
             taken[j] = 1;
         }
-        if (filled < R) {             // duplicates shrank the candidate list: undo and defer
-            for (int32_t k = 0; k < filled; ++k) taken[out[k]] = 0;
-            late.push_back(i);
-            continue;
+        int32_t expand = 1;           // members[expand..) have not been expanded yet
+        while (filled < R) {
+            if (expand < filled) {
+                const int32_t m = out[expand++];
+                for (int32_t e = rowptr[m]; e < rowptr[m + 1] && filled < R; ++e) {
+                    const int32_t j = col[e];
+                    if (j < N && !taken[j]) { out[filled++] = j; taken[j] = 1; }
+                }
+            } else {
+                while (next_free < order.size() && taken[order[next_free]]) ++next_free;
+                if (next_free == order.size()) break;
+                const int32_t j = order[next_free];
+                out[filled++] = j;
+                taken[j] = 1;
+            }
         }
-        ++g;
-    }
-    // 3. leftovers, chunked in BFS order
-    int32_t slot = 0;
-    for (int32_t i : late) {
-        if (taken[i]) continue;
-        grp_rows[(size_t)g * R + slot] = i;
-        taken[i] = 1;
-        if (++slot == R) { slot = 0; ++g; }
-    }
-    if (slot) {
-        for (; slot < R; ++slot) grp_rows[(size_t)g * R + slot] = -1;
+        for (; filled < R; ++filled) out[filled] = -1;      // only the last group can be short
         ++g;
     }
     SGP_REQUIRE(g == n_groups, SGP_EINVAL, "sgp_group_rows: internal error, %d groups != %d", g, n_groups);

@@ -187,7 +187,7 @@ template <int NFC, bool HALO, int kTcProducerWarps>
 __global__ void __launch_bounds__((kTcSplitWarps + kTcProducerWarps + kTcIssuers) * 32, 1)
 spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ grp_rows,
                    const int32_t* __restrict__ cols, const float* __restrict__ bimg,
-                   int n_groups, int n_work,
+                   int n_groups, int n_work, int group_major,
                    const float* __restrict__ src, int64_t s_ts, uint32_t s_nb /* row stride, BYTES */,
                    const float* __restrict__ src2, int64_t s2_ts, uint32_t s2_nb, int n_split,
                    float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int Tc, int* err, long long* trace) {
@@ -239,13 +239,32 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
     constexpr uint32_t kBOff = kTcStages * kTcStageBytes;               // slab images after the ring
+    // Work order of this (persistent) CTA, s-th work item:
+    //   group_major == 0 (default): w = blockIdx.x + s * gridDim.x, (time block, group) =
+    //     (w / n_groups, w % n_groups): all CTAs sweep the groups of one time block together, so
+    //     neighbouring groups' gathers share panel rows in L2 for as long as the sweep lasts;
+    //   group_major == 1: the CTA's groups are blockIdx.x, + gridDim.x, ... and each runs ALL time
+    //     blocks back to back (slab images stay in L2) — measured slower (133 vs 104 us per
+    //     hop-panel at C4): CTAs drift apart by whole work items and then share nothing.
+    const int ny = n_work / n_groups;
+    auto work_item = [&](int s_, int& g_, int& t_begin_) -> bool {
+        if (group_major) {
+            const int k_ = s_ / ny;
+            g_ = blockIdx.x + k_ * gridDim.x;
+            t_begin_ = (s_ - k_ * ny) * TB;
+            return g_ < n_groups;
+        }
+        const int w_ = blockIdx.x + s_ * gridDim.x;
+        const int y_ = w_ / n_groups;
+        g_ = w_ - y_ * n_groups;
+        t_begin_ = y_ * TB;
+        return w_ < n_work;
+    };
 
-    // The CTA is persistent: work item w = (time block y, group g), w = y * n_groups + g, taken
-    // round-robin (w = blockIdx.x, + gridDim.x, ...) so that concurrently running CTAs work on
-    // neighbouring groups of the same time block.  All barrier phases run on counters that
-    // continue across work items: `it` items, `cc` chunks, (bi, bph) slab buffers, `wn` work
-    // items with at least one chunk.  The producers simply run on into the next work item while
-    // the split warps drain the accumulators of the previous one.
+    // The CTA is persistent.  All barrier phases run on counters that continue across work
+    // items: `it` items, `cc` chunks, (bi, bph) slab buffers, `wn` work items with at least one
+    // chunk.  The producers simply run on into the next work item while the split warps drain the
+    // accumulators of the previous one.
     if (warp >= kTcSplitWarps && warp < kTcSplitWarps + kTcProducerWarps) {
         // ================= producers: warp p gathers the items with accumulator index a = p ======
         // One item = 32 source rows x 512 bytes: a cp.async per row, the 32 lanes covering its 128
@@ -265,19 +284,19 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         bool ok = true;
         // lane j holds the source-row id j of the NEXT chunk, fetched while the current one is issued
         int coln = 0;
-        auto first_chunk_of = [&](int w) -> long long {        // first chunk of the next non-empty work item
-            for (; w < n_work; w += gridDim.x) {
-                const int g2 = w % n_groups;
+        auto first_chunk_of = [&](int s2) -> long long {       // first chunk of the next non-empty work item
+            int g2, tb2;
+            for (; work_item(s2, g2, tb2); ++s2)
                 if (chunk_ptr[g2 + 1] > chunk_ptr[g2]) return chunk_ptr[g2];
-            }
             return -1;
         };
         {
-            const long long f = first_chunk_of(blockIdx.x);
+            const long long f = first_chunk_of(0);
             if (f >= 0) coln = __ldg(cols + (size_t)f * kTcKC + lane);
         }
-        for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
-            const int g = w % n_groups, t_begin = (w / n_groups) * TB;
+        for (int ws = 0; ok; ++ws) {
+            int g, t_begin;
+            if (!work_item(ws, g, t_begin)) break;
             const int c_beg = chunk_ptr[g], n_chunks = chunk_ptr[g + 1] - c_beg;
             const int t = min(t_begin + pw / NFC, Tc - 1);             // out-of-range steps are clamped
             const char* b1 = reinterpret_cast<const char*>(src + (size_t)t * s_ts + (pw % NFC) * 128) + lane * 16;
@@ -289,7 +308,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                 // byte offset of row `lane` inside its source (bit 31: the row lives in src2)
                 const uint32_t mine = in2 ? (((uint32_t)(col - n_split) * s2_nb) | 0x80000000u) : (uint32_t)col * s_nb;
                 {
-                    const long long nxt = (c + 1 < n_chunks) ? (long long)(c_beg + c + 1) : first_chunk_of(w + gridDim.x);
+                    const long long nxt = (c + 1 < n_chunks) ? (long long)(c_beg + c + 1) : first_chunk_of(ws + 1);
                     if (nxt >= 0) coln = __ldg(cols + (size_t)nxt * kTcKC + lane);
                 }
                 const int s = it & (kTcStages - 1);
@@ -325,8 +344,9 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
         int it0 = 0, cc = 0, wn = 0;                               // items, chunks, non-empty work items so far
         bool ok = true;
-        for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
-            const int g = w % n_groups, t_begin = (w / n_groups) * TB;
+        for (int ws = 0; ok; ++ws) {
+            int g, t_begin;
+            if (!work_item(ws, g, t_begin)) break;
             const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
             // destination rows of the group (lane j holds rows j and 32 + j), for the epilogue
             const int my_row0 = __ldg(grp_rows + (size_t)g * kTcR + lane);
@@ -458,8 +478,9 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             const int q = warp - (kTcSplitWarps + kTcProducerWarps);
             int bi = 0, bph = 0, cc = 0, wn = 0, itn = q;
             bool ok = true;
-            for (int w = blockIdx.x; w < n_work && ok; w += gridDim.x) {
-                const int g = w % n_groups;
+            for (int ws = 0; ok; ++ws) {
+                int g, t_begin_unused;
+                if (!work_item(ws, g, t_begin_unused)) break;
                 const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
 #pragma unroll 1
                 for (int c = 0; c < n_chunks && ok; ++c, ++cc) {
@@ -532,14 +553,16 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
     SGP_REQUIRE(dst_n_stride > 0 && dst_n_stride * 4 < (1ll << 32), SGP_EUNSUPPORTED, "sgp_spmm_rbu_tc: dst row stride too large");
     const uint32_t s_nb = (uint32_t)(src_n_stride * 4), s2_nb = (uint32_t)(src2_n_stride * 4);
     const int n_work = n_groups * ny;
-    const int grid = n_work < kNumSMs ? n_work : kNumSMs;        // persistent: one CTA per SM
+    const int group_major = getenv("SGP_B200_TC_ORDER") && getenv("SGP_B200_TC_ORDER")[0] == 'g';
+    const int n_par = group_major ? n_groups : n_work;
+    const int grid = n_par < kNumSMs ? n_par : kNumSMs;          // persistent: one CTA per SM
     long long* trace_ptr = getenv("SGP_B200_TC_TRACE") ? (long long*)strtoull(getenv("SGP_B200_TC_TRACE"), nullptr, 10) : nullptr;
 #define SGP_TC3(NFC_, HALO_, PW_)                                                                      \
     do {                                                                                               \
         SGP_CUDA(cudaFuncSetAttribute(spmm_rbu_tc_kernel<NFC_, HALO_, PW_>,                            \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));     \
         spmm_rbu_tc_kernel<NFC_, HALO_, PW_><<<grid, (kTcSplitWarps + PW_ + kTcIssuers) * 32, kTcSmem, as_stream(stream)>>>( \
-            chunk_ptr, grp_rows, cols, bimg, n_groups, n_work, src, src_t_stride, s_nb, src2,          \
+            chunk_ptr, grp_rows, cols, bimg, n_groups, n_work, group_major, src, src_t_stride, s_nb, src2, \
             src2_t_stride, s2_nb, n_split, dst, dst_t_stride, dst_n_stride, Tc, err_flag, trace_ptr);  \
     } while (0)
 #define SGP_TC(NFC_, HALO_)                                                                            \
