@@ -91,6 +91,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -187,7 +192,7 @@ template <int NFC, bool HALO, int kTcProducerWarps>
 __global__ void __launch_bounds__((kTcSplitWarps + kTcProducerWarps + kTcIssuers) * 32, 1)
 spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ grp_rows,
                    const int32_t* __restrict__ cols, const float* __restrict__ bimg,
-                   int n_groups, int n_work, int group_major,
+                   int n_groups, int n_work, int group_major, int gather_policy,
                    const float* __restrict__ src, int64_t s_ts, uint32_t s_nb /* row stride, BYTES */,
                    const float* __restrict__ src2, int64_t s2_ts, uint32_t s2_nb, int n_split,
                    float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int Tc, int* err, long long* trace) {
@@ -278,7 +283,8 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         // The chunk's slab images ride on item a = 0's barrier as one 16 KB TMA bulk copy.
         static_assert(kTcProducerWarps == kTcAcc, "one producer warp per accumulator index");
         const int pw = warp - kTcSplitWarps;
-        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+        const uint64_t pol_stream = l2_policy_evict_first();
+        const uint64_t pol_keep = gather_policy == 1 ? l2_policy_evict_normal() : gather_policy == 2 ? l2_policy_evict_first() : l2_policy_evict_last();
         const uint32_t full0 = smem_u32(&full[0]), dst0 = smem_base + lane * 16;
         int it = pw, bi = 0, bph = 0;
         bool ok = true;
@@ -554,6 +560,7 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
     const uint32_t s_nb = (uint32_t)(src_n_stride * 4), s2_nb = (uint32_t)(src2_n_stride * 4);
     const int n_work = n_groups * ny;
     const int group_major = getenv("SGP_B200_TC_ORDER") && getenv("SGP_B200_TC_ORDER")[0] == 'g';
+    const int gather_policy = getenv("SGP_B200_TC_GATHER") ? atoi(getenv("SGP_B200_TC_GATHER")) : 0;   // 0 evict_last, 1 normal, 2 evict_first
     const int n_par = group_major ? n_groups : n_work;
     const int grid = n_par < kNumSMs ? n_par : kNumSMs;          // persistent: one CTA per SM
     long long* trace_ptr = getenv("SGP_B200_TC_TRACE") ? (long long*)strtoull(getenv("SGP_B200_TC_TRACE"), nullptr, 10) : nullptr;
@@ -562,7 +569,7 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
         SGP_CUDA(cudaFuncSetAttribute(spmm_rbu_tc_kernel<NFC_, HALO_, PW_>,                            \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));     \
         spmm_rbu_tc_kernel<NFC_, HALO_, PW_><<<grid, (kTcSplitWarps + PW_ + kTcIssuers) * 32, kTcSmem, as_stream(stream)>>>( \
-            chunk_ptr, grp_rows, cols, bimg, n_groups, n_work, group_major, src, src_t_stride, s_nb, src2, \
+            chunk_ptr, grp_rows, cols, bimg, n_groups, n_work, group_major, gather_policy, src, src_t_stride, s_nb, src2, \
             src2_t_stride, s2_nb, n_split, dst, dst_t_stride, dst_n_stride, Tc, err_flag, trace_ptr);  \
     } while (0)
 #define SGP_TC(NFC_, HALO_)                                                                            \
