@@ -225,7 +225,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         for (int b = 0; b < kTcABufs; ++b) {
             mbar_init(&ready[b], 4);
             mbar_init(&afree[b], 1);
-            mbar_init(&accfree[b], 4);
+            mbar_init(&accfree[b], kTcSplitWarps);      // every split warp drains a slice of every accumulator
         }
         for (int b = 0; b < kTcBBufs; ++b) {
             mbar_init(&bfree[b], kTcIssuers);
@@ -345,11 +345,48 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp < kTcSplitWarps) {
         // ================= split warps: stage (smem) -> A hi | lo tiles (TMEM); epilogue =======
-        // two groups of 4 warps; group G takes the items / accumulators with (a & 1) == G
+        // four groups of 4 warps; group G takes the items of accumulator a = G (warp & 3 = TMEM lane quarter)
         const int grp = warp >> 2, m = tid & 127;                  // m = feature = TMEM lane
         const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
         int it0 = 0, cc = 0, wn = 0;                               // items, chunks, non-empty work items so far
         bool ok = true;
+        // one chunk's item of my accumulator: ring stage -> A tile (hi | lo) in TMEM
+        auto convert_item = [&]() -> bool {
+            const int a = grp;
+            const int it = it0 + a, s = it & (kTcStages - 1);
+            if (!warp_wait(&full[s], (it >> 3) & 1, &abort_s, err, lane)) return false;
+            if ((warp & 3) == 0) SGP_TRACE(2, it);
+            if (cc > 0 && !warp_wait(&afree[a], (cc - 1) & 1, &abort_s, err, lane)) return false;
+            if ((warp & 3) == 0) SGP_TRACE(3, it);
+            const uint32_t rs = smem_base + s * kTcStageBytes + m * 4;     // row-major stage: [k][feature]
+            const uint32_t ta = lane_addr + kTcAOff + a * 64;
+#pragma unroll
+            for (int k0 = 0; k0 < kTcKC; k0 += 16) {       // two halves: 32 live registers, not 64
+                uint32_t hv[16], lv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    float x;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(rs + (k0 + k) * 512));
+                    hv[k] = __float_as_uint(x);    // the tensor core ignores the low 13 mantissa bits
+                    lv[k] = __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+                }
+                SGP_TMEM_ST16(ta + k0, hv);
+                SGP_TMEM_ST16(ta + 32 + k0, lv);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&ready[a]);
+                mbar_arrive(&empty[s]);
+            }
+            if ((warp & 3) == 0) SGP_TRACE(4, it);
+            SGP_TRACE(8 + (warp & 3), it);
+            ++cc;
+            it0 += kTcAcc;
+            return true;
+        };
+        bool primed = false;        // chunk 0 of the current work item was converted before the previous drain
         for (int ws = 0; ok; ++ws) {
             int g, t_begin;
             if (!work_item(ws, g, t_begin)) break;
@@ -357,38 +394,18 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             // destination rows of the group (lane j holds rows j and 32 + j), for the epilogue
             const int my_row0 = __ldg(grp_rows + (size_t)g * kTcR + lane);
             const int my_row1 = __ldg(grp_rows + (size_t)g * kTcR + 32 + lane);
-            for (int c = 0; c < n_chunks && ok; ++c, ++cc, it0 += kTcAcc) {
 #pragma unroll 1
-                for (int a = grp; a < kTcAcc; a += kTcSplitGroups) {
-                    const int it = it0 + a, s = it & (kTcStages - 1);
-                    if (!warp_wait(&full[s], (it >> 3) & 1, &abort_s, err, lane)) { ok = false; break; }
-                    if ((warp & 3) == 0) SGP_TRACE(2, it);
-                    if (cc > 0 && !warp_wait(&afree[a], (cc - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
-                    if ((warp & 3) == 0) SGP_TRACE(3, it);
-                    const uint32_t rs = smem_base + s * kTcStageBytes + m * 4;     // row-major stage: [k][feature]
-                    const uint32_t ta = lane_addr + kTcAOff + a * 64;
-#pragma unroll
-                    for (int k0 = 0; k0 < kTcKC; k0 += 16) {       // two halves: 32 live registers, not 64
-                        uint32_t hv[16], lv[16];
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) {
-                            float x;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(rs + (k0 + k) * 512));
-                            hv[k] = __float_as_uint(x);    // the tensor core ignores the low 13 mantissa bits
-                            lv[k] = __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
-                        }
-                        SGP_TMEM_ST16(ta + k0, hv);
-                        SGP_TMEM_ST16(ta + 32 + k0, lv);
-                    }
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(&ready[a]);
-                        mbar_arrive(&empty[s]);
-                    }
-                    if ((warp & 3) == 0) SGP_TRACE(4, it);
-                    SGP_TRACE(8 + (warp & 3), it);
+            for (int c = primed ? 1 : 0; c < n_chunks && ok; ++c) ok = convert_item();
+            primed = false;
+            if (!ok) break;
+            // Prime the next work item's first chunk BEFORE draining: its MMAs then start as soon
+            // as the first accumulator is free, under the rest of the drain.
+            {
+                int g2, tb2;
+                if (work_item(ws + 1, g2, tb2) && chunk_ptr[g2 + 1] > chunk_ptr[g2]) {
+                    ok = convert_item();
+                    primed = true;
+                    if (!ok) break;
                 }
             }
             if (!ok) break;
@@ -400,42 +417,41 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             // Kept lean on purpose: the drain is exposed (the next work item's MMAs need the
             // accumulators), and its first version — a shuffle, a 64-bit multiply and a branch per
             // row, ~15 dependent instructions — took 9k cycles per work item (38% of the hop).
+            // All 16 warps drain accumulator 0 first, then 1, 2, 3 (group G takes rows [16 G, 16 G + 16)
+            // of each), so that accfree[0] fires after a quarter of the drain and the next work
+            // item's MMAs start under the rest of it.
             const uint32_t d_nb = (uint32_t)d_ns * 4u;           // row stride in bytes (host checks < 2^32)
+            int rows[16];
+#pragma unroll
+            for (int e2 = 0; e2 < 16; ++e2)
+                rows[e2] = __shfl_sync(0xffffffffu, (grp < 2) ? my_row0 : my_row1, (grp & 1) * 16 + e2);
 #pragma unroll 1
-            for (int a = grp; a < kTcAcc; a += kTcSplitGroups) {
+            for (int a = 0; a < kTcAcc; ++a) {
                 const int t = t_begin + a / NFC;
                 const bool t_ok = t < Tc;
                 const char* dp = reinterpret_cast<const char*>(dst + (size_t)min(t, Tc - 1) * d_ts + (a % NFC) * 128 + (warp & 3) * 32 + lane);
-#pragma unroll
-                for (int j = 0; j < kTcR; j += 16) {
-                    uint32_t v[16];
-                    if (n_chunks > 0) {
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
-                                       "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
-                                       "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                                     : "r"(lane_addr + a * kTcR + j));
-                    } else {
-#pragma unroll
-                        for (int e2 = 0; e2 < 16; ++e2) v[e2] = 0u;      // group without entries: zero rows
-                    }
-                    int rows[16];
-#pragma unroll
-                    for (int e2 = 0; e2 < 16; ++e2)
-                        rows[e2] = __shfl_sync(0xffffffffu, (j < 32) ? my_row0 : my_row1, (j & 31) + e2);
-                    if (n_chunks > 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int e2 = 0; e2 < 16; ++e2) {
-                        if (t_ok && rows[e2] >= 0)
-                            asm volatile("st.global.cs.b32 [%0], %1;"      // streaming (evict-first): written once, read by the next hop's launch
-                                         :: "l"(dp + (uint64_t)(uint32_t)rows[e2] * d_nb), "r"(v[e2]) : "memory");
-                    }
-                }
-                if (n_chunks > 0) {       // accumulator a may be overwritten by the next work item
+                uint32_t v[16];
+                if (n_chunks > 0) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                                   "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                                   "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                 : "r"(lane_addr + a * kTcR + grp * 16));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // my part of accumulator a is in registers: it may be overwritten by the next work item
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&accfree[a]);
+                } else {
+#pragma unroll
+                    for (int e2 = 0; e2 < 16; ++e2) v[e2] = 0u;          // group without entries: zero rows
+                }
+#pragma unroll
+                for (int e2 = 0; e2 < 16; ++e2) {
+                    if (t_ok && rows[e2] >= 0)
+                        asm volatile("st.global.cs.b32 [%0], %1;"      // streaming (evict-first): written once, read by the next hop's launch
+                                     :: "l"(dp + (uint64_t)(uint32_t)rows[e2] * d_nb), "r"(v[e2]) : "memory");
                 }
             }
             if (n_chunks > 0) ++wn;
