@@ -282,10 +282,21 @@ def run_own(args, cfg):
     scan_n, scan_ms = summ.get("scan", (0, 0.0))
     scan_flops = N * T * (2 * H * (Fin + H) + 6 * H) * args.steps
     fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    # measured DRAM traffic of the same kernel (one ncu --set full capture, profiles/r1_traffic.json),
+    # scaled from the captured launch's time steps to this run's
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)
+        rec = tr.get("spmm_rbu_tc_kernel") if fwd.tc is not None else None
+        if rec and tr.get("workload") == args.workload:
+            traffic = (rec["dram_read_bytes"] + rec["dram_write_bytes"]) * step_T / rec["timesteps"]
+    except (OSError, ValueError, KeyError):
+        traffic = None
     roofline = dict(bound="hbm", kernel=("spmm_rbu_tc_kernel (tcgen05, 3xTF32)" if fwd.tc is not None else
                             ("spmm_rbu_v3<%d>" % fwd.rbu.R) if fwd.rbu is not None else "spmm_csr_vec"),
                     achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                    peak_source=peaks["source"], traffic=None,
+                    peak_source=peaks["source"], traffic=traffic,
                     algorithmic_bytes_per_launch=bytes_per_launch, timesteps_per_launch=step_T,
                     avg_launch_ms=avg_ms, launches_timed=n_full,
                     gflops=flops_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0,

@@ -289,6 +289,31 @@ def test_spmm_tensor_core_vs_oracle(F, n, k):
     assert err < 2e-5, err
 
 
+@pytest.mark.parametrize("F", [128, 256])
+def test_spmm_tensor_core_halo_columns(F):
+    """The sharded encoder's operator: own rows x [own | halo] columns, halo rows read from a second
+    buffer with its own strides (src2 / n_split of sgp_spmm_rbu_tc).  Checked against the oracle on
+    the unsplit operator."""
+    n, n_own, k = 1500, 900, 30
+    ei, ew = sensor_knn(n, k, seed=F)
+    rowptr, col, val = O.build_operator(ei, ew, n, set_diag=False)
+    # rows [0, n_own) keep their global column ids: columns >= n_own are "halo"
+    rp, cl, vl = rowptr[:n_own + 1], col[:rowptr[n_own]], val[:rowptr[n_own]]
+    csr = ops.Csr(torch.from_numpy(rp.astype(np.int32)).to(DEV), torch.from_numpy(cl.astype(np.int32)).to(DEV),
+                  torch.from_numpy(vl.astype(np.float32)).to(DEV), n_own)
+    tc = ops.tc_build(csr, n_cols=n)
+    T = 5
+    x = np.random.default_rng(F + 1).standard_normal((T, n, F)).astype(np.float32)
+    own = torch.zeros(T, n_own, 2 * F, device=DEV)
+    own[..., :F] = torch.from_numpy(x[:, :n_own]).to(DEV)
+    # halo rows live node-major in their own buffer (as the all-to-all leaves them)
+    halo = torch.from_numpy(x[:, n_own:]).to(DEV).permute(1, 0, 2).contiguous().permute(1, 0, 2)
+    ops.spmm_tc(tc, own[..., :F], own[..., F:], halo=halo, n_split=n_own)
+    ops.tc_check(tc)
+    ref = O.spmm(rowptr, col, val, x, impl="c")[:, :n_own]
+    assert_blocks_close(own[..., F:].cpu().numpy(), ref, F)
+
+
 def test_spmm_tensor_core_irregular_graph_empty_rows_duplicates():
     n = 700
     ei, ew = random_graph(n, 5000, seed=3)
