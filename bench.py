@@ -214,7 +214,7 @@ def run_own(args, cfg):
 
     if world > 1:
         from sgp_b200 import sharded
-        return sharded.bench(args, cfg, rank, world, dev, peaks, config_dict, METRIC, UNIT)
+        return sharded.bench(args, cfg, rank, world, dev, peaks, config_dict, METRIC, UNIT, clock_sampler=ClockSampler)
 
     N, T, H, K, Fin = cfg["N"], cfg["T"], cfg["H"], cfg["K"], cfg["Fin"]
     F, D = H, (K + 1) * H

@@ -227,7 +227,7 @@ class RowShardedEncoder:
 # --------------------------------------------------------------------------------------------
 # bench.py, N > 1
 # --------------------------------------------------------------------------------------------
-def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit):
+def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_sampler=None):
     """Strong scaling of the bench workload: the same N x T series, rows sharded over `world`
     GPUs.  value = N*T / max-over-ranks device time."""
     import json
@@ -243,7 +243,8 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit):
                               bidirectional=False, alpha_decay=False, global_attr=False)
     sh = RowShardedEncoder(enc, torch.from_numpy(ei), torch.from_numpy(ew), N, dev)
     x = sensor_signal(T, N, seed=1, exogenous=Fin == 3)
-    x_own = torch.from_numpy(np.ascontiguousarray(x[:, sh.own])).to(dev)
+    x_host = torch.from_numpy(np.ascontiguousarray(x[:, sh.own])).pin_memory()     # this rank's rows, pinned
+    x_own = x_host.to(dev)
     del x
     D = enc.output_size
     step = args.chunk or max(1, min(T, (args.chunk_mb << 20) // max(sh.plan.n_own * D * 4, 1)))
@@ -256,6 +257,9 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit):
         one_pass()
     torch.cuda.synchronize()
     acc.zero_()
+    sampler = clock_sampler(dev.index) if (clock_sampler is not None and rank == 0) else None
+    if sampler is not None:
+        sampler.start()
     dist.barrier()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -266,8 +270,35 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit):
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
+    clocks = sampler.stop() if sampler is not None else None
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # ---- end to end: every step copies this rank's rows of the series from pinned host memory
+    # and reads the checksum back; the operator / halo plan is built once (it is per graph)
+    chk_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    chk_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def one_pass_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        chk_dev.zero_()
+        sh.encode_stream(xd, lambda t0, t1, chunk: ops.checksum(chunk, chk_dev), chunk_steps=step)
+        chk_host.copy_(chk_dev, non_blocking=True)
+
+    one_pass_e2e()
+    torch.cuda.synchronize()
+    dist.barrier()
+    n_e2e = max(1, min(args.steps, 2))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n_e2e):
+        one_pass_e2e()
+    f1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_e2e = torch.tensor([f0.elapsed_time(f1) / n_e2e], device=dev)
+    dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    h2d = torch.tensor([float(x_host.numel() * 4)], device=dev, dtype=torch.float64)
+    dist.all_reduce(h2d)
     launches = torch.tensor([_lib.launch_count() - l0], device=dev)
     dist.all_reduce(launches)
     halo = torch.tensor([sh.plan.n_halo, sh.plan.n_own], device=dev, dtype=torch.float64)
@@ -283,8 +314,11 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit):
                         chunk_steps=step, halo_rows_per_owned_row=float(halo[0] / halo[1]),
                         exchange="all_to_all_v of halo rows per hop (NCCL), 2 chunks in flight")),
                     roofline=None, cpu_baseline=None,
-                    e2e=dict(value=value, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=8,
-                             note="device-resident sharded input; see the N=1 line for the host-buffer path"),
-                    gpu_launches=int(launches), checksum=float(acc) / args.steps)
+                    e2e=dict(value=N * T / (float(ms_e2e) * 1e-3), unit=unit, h2d_bytes_per_step=int(h2d),
+                             d2h_bytes_per_step=8 * world, ms_per_step=float(ms_e2e), checksum=float(chk_host),
+                             note="per step every rank copies its rows of x from pinned host memory, encodes "
+                                  "(scan + halo exchange + K hops per chunk) and reads its checksum back; the "
+                                  "operator and halo plan are per graph and built once, outside the step"),
+                    clocks=clocks, gpu_launches=int(launches), checksum=float(acc) / args.steps)
         print(json.dumps(line))
     dist.destroy_process_group()
