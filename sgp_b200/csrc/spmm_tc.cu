@@ -2,39 +2,39 @@
 //
 // Same contract as sgp_spmm_rbu (dst[t, i, :] = sum_e val[e] * src[t, col[e], :], replacing
 // `x = adj @ x` of lib/sgp_preprocessing.py:200-203), different formulation: rows are grouped 64
-// at a time (the same locality-greedy groups as the RBU format) and a hop becomes, per group,
+// at a time (compact blobs, sgp_group_rows) and a hop becomes, per group,
 //     D[f, r] = sum_u  X[u, f] * B[r, u]        f: 128 features, r: 64 rows, u: union columns
 // i.e. a dense [128 x U] x [U x 64] GEMM whose A operand is the GATHERED source rows and whose B
 // operand is the group's slab of operator values (zero where a row lacks the column).  The zero
 // fill that costs the CUDA-core RBU kernel 1.8x of its FFMA2 budget is free here, while the
-// gather traffic drops another 2x (U/R = 5.4 at R = 64 against 11.3 at R = 16 on the 100-NN
-// graph), which is what lets the hop approach the HBM roofline.
+// gather traffic drops another 2x (U/R = 4.96 at R = 64 against 11.2 at R = 16 on the 100-NN
+// graph).
 //
 //   * A = X^T chunk (32 gathered rows x 128 features), fed to the MMA from TMEM (TS mode: lane =
 //     feature, column = gathered row).  The gather is cp.async (16 bytes per lane, a warp per 512-byte
 //     row piece) into a row-major ring stage; the copies signal the stage's mbarrier themselves
 //     (cp.async.mbarrier.arrive.noinc), so the whole 8-stage ring stays in flight.
 //   * B = slab chunk (64 rows x 32 columns), K-major SWIZZLE_128B, pre-swizzled at operator build
-//     time, streamed linearly with cp.async and reused for 8 accumulators (4 time steps x 2 feature
-//     chunks at F = 256) so that its HBM traffic is amortised.
+//     time (hi | lo images, 16 KB), one TMA bulk copy per chunk, reused by the chunk's 4 items
+//     (2 time steps x 2 feature chunks at F = 256).
 //   * precision: 3xTF32.  hi = x with the low 13 mantissa bits cleared, lo = x - hi, and
 //     D += Ah*Bh + Al*Bh + Ah*Bl with fp32 accumulation in TMEM.  The tensor core ignores the low
 //     13 bits of a tf32 operand, so the gathered fp32 rows are used as Ah as they are and only Al
-//     is produced (one shared-memory pass per tile); B is split at operator build time.
-//     Measured 1e-6..3e-6 relative (tools/microbench/umma_tf32_test.cu), well inside 1e-4.
-//   * accumulators: 8 x [128 lanes x 64 columns] fp32 = all 512 TMEM columns, one CTA per SM.
-//   * warp-specialised pipeline per item (chunk, accumulator), all hand-offs through mbarriers:
-//     4 producer warps gather with cp.async into an 8-stage ring (up to 7 items = 112 KB in flight
-//     per SM), two groups of 4 "split" warps alternate items and write the lo tiles (4 of them),
-//     one elected lane of the MMA warp issues 12 tcgen05.mma per item and tcgen05.commit's the
-//     barriers that recycle the ring stage and the lo tile.  Lessons that shaped it (profiles/):
-//     fence.proxy.async drains a thread's outstanding cp.async (so gathers and fences live in
-//     different warps); 128 threads arriving/polling on one mbarrier serialise (warp-level
-//     arrive); `lane == 0` makes ptxas wrap every MMA in an R2UR waterfall (elect.sync does not);
-//     a role's loop must stay small (three roles share one 32 KB instruction cache).
-//   * measured limit: shared-memory bandwidth (operand fetches of 12 N=64 MMAs = 72 KB + 48 KB
-//     of gather / lo-pass traffic per item at 128 B/clk).
-// Bound: HBM.  Algorithmic bytes per hop-panel 8 nnz + 4(N+1) + 8 N F (285 MB at C4).
+//     is computed (in registers, on the way from the ring stage to TMEM); B is split at operator
+//     build time.  Measured 1e-6..3e-6 relative (tools/microbench/umma_tf32_test.cu).
+//   * TMEM: 4 accumulators of [128 lanes x 64 columns] + 4 A tiles of (32 hi + 32 lo) columns =
+//     all 512 columns, one persistent CTA per SM.
+//   * 22 warps, all hand-offs through mbarriers: 4 producer warps (one per accumulator index), 16
+//     "split" warps (4 groups x TMEM lane quarter: ring stage -> hi | lo -> tcgen05.st, and the
+//     accumulator drain), 2 MMA-issuing warps (one elected thread each, 12 tcgen05.mma per item).
+//     Lessons that shaped it (profiles/r1_trace_tc.txt): a lone warp issues dependent instructions
+//     ~5 cycles apart, so every role's per-item loop must be a few dozen instructions (barrier
+//     addresses precomputed, nothing recomputed per item, no trace code compiled in); `lane == 0`
+//     makes ptxas wrap every MMA in an R2UR waterfall (elect.sync does not); wait_group-based
+//     signalling keeps only `lag` stages in flight; a TMA bulk copy per 512-byte row costs ~75
+//     cycles per request; 128 threads arriving/polling on one mbarrier serialise.
+// Bound: HBM (algorithmic bytes per hop-panel 8 nnz / Tb + 4(N+1) / Tb + 8 N F: 210 MB at C4, Tb =
+// 16); today the tensor pipe (384 cycles per item) plus the exposed accumulator drain.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -174,16 +174,18 @@ __device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volati
                     "r"(arr[24]), "r"(arr[25]), "r"(arr[26]), "r"(arr[27]), "r"(arr[28]), "r"(arr[29]),        \
                     "r"(arr[30]), "r"(arr[31]) : "memory")
 
-// Warp roles (13 warps): warps 0-7 "split" in two groups of four that alternate items (warp & 3 =
-// the TMEM lane quarter the warp may touch), warps 8-11 "producer" (cp.async gathers + slab
-// images), warp 12 issues the MMAs.
+// Warp roles (22 warps): warps 0-15 "split" in four groups of four (group = accumulator index,
+// warp & 3 = the TMEM lane quarter the warp may touch), warps 16-19 "producer" (cp.async gathers;
+// producer 0 also fetches the slab images), warps 20-21 issue the MMAs (items a = q mod 2).
 // An item is (chunk c, accumulator a); i = 4c + a; ring stage s = i % 8; A tile = a.
-// mbarriers: full[s]  producers -> split  : stage s holds item i's gathered rows (+ slab images)
+// mbarriers: full[s]  producer (its cp.asyncs) -> split : stage s holds item i's gathered rows
 //            empty[s] split -> producers  : the split group has copied stage s into TMEM
 //            ready[a] split -> MMA        : A tile a (hi | lo) is in TMEM
 //            afree[a] MMA (tcgen05.commit) -> split : the MMAs reading A tile a have completed
-//            bfree[c%3] MMA (tcgen05.commit) -> producers : slab buffer may be overwritten
-//            done     MMA -> epilogue
+//            bfull[c%3] producer 0 (TMA bytes) -> MMA : the chunk's slab images have landed
+//            bfree[c%3] MMA (tcgen05.commit, both issuers) -> producer 0 : slab buffer may be overwritten
+//            done     MMA (both issuers) -> split : the work item's accumulators are complete
+//            accfree[a] split (16 warps) -> MMA : accumulator a has been read out
 // BOTH MMA operands' A side lives in TMEM: the split warps read a gathered stage once from shared
 // memory (thread = feature = TMEM lane, 32 k values), form hi / lo in registers and tcgen05.st
 // them; the 12 MMAs of an item then fetch only the 2 KB slab operand from shared memory each, so

@@ -173,3 +173,25 @@ def test_synthetic_generators_shapes():
     x = sensor_signal(50, 7)
     assert x.shape == (50, 7, 3) and x.dtype == np.float32
     np.testing.assert_allclose(x[:, 0, 1], x[:, 3, 1])             # exogenous broadcast over nodes
+
+
+def test_group_rows_has_no_scattered_leftover_groups():
+    """Every 64-row group of a kNN graph must be a compact blob: the union of its rows' columns
+    stays near the median (a deferred-leftovers grouping produced 10x outliers that cost 20% of
+    the hop)."""
+    from sgp_b200 import ops
+    from sgp_b200.synthetic import sensor_knn
+    n, k, R = 6000, 40, 64
+    ei, ew = sensor_knn(n, k, seed=3)
+    row, col = ei[1].astype(np.int64), ei[0].astype(np.int64)
+    order = np.argsort(row * n + col, kind="stable")
+    row, col, val = row[order], col[order], ew[order].astype(np.float32)
+    rowptr = np.zeros(n + 1, np.int64)
+    np.add.at(rowptr, row + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    g = ops.group_rows_host(rowptr.astype(np.int32), col.astype(np.int32), val, n, R)
+    assert sorted(g[g >= 0].tolist()) == list(range(n))
+    assert (g[:-1] >= 0).all()                     # only the last group may be short
+    unions = np.array([len(np.unique(np.concatenate([col[rowptr[r]:rowptr[r + 1]] for r in gr[gr >= 0]])))
+                       for gr in g])
+    assert unions.max() <= 2.5 * np.median(unions), (unions.max(), np.median(unions))
