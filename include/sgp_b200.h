@@ -159,9 +159,9 @@ int sgp_spmm_rbu_halo(const int32_t* grp_ptr, const int32_t* grp_rows, const int
 
 /* Tensor-core hop (tcgen05, 3xTF32, fp32-accurate): rows grouped 64 at a time, union columns padded
  * to chunks of 32.  chunk_ptr [n_groups+1] (in chunks), grp_rows [n_groups, 64] (-1 = padding),
- * cols [total_chunks*32] source row ids, bimg [total_chunks][2][64*32] the chunk's operator values
- * as tf32 hi / lo images in the K-major SWIZZLE_128B shared-memory layout (built by
- * sgp_b200/ops.py::tc_build).  F in {128, 256, 512}.  *err_flag (device int) is set to 1 if
+ * cols [total_chunks*32] source row ids, bimg [total_chunks][64*32] the chunk's operator values
+ * (fp32) in the K-major SWIZZLE_128B shared-memory layout (built by sgp_b200/ops.py::tc_build; the
+ * kernel splits them into tf32 hi / lo).  F in {128, 256, 512}.  *err_flag (device int) is set to 1 if
  * an internal barrier times out.  src2 / n_split as in sgp_spmm_halo. */
 int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int32_t* cols,
                     const float* bimg, int n_groups,

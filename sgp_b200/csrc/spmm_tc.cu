@@ -14,9 +14,9 @@
 //     feature, column = gathered row).  The gather is cp.async (16 bytes per lane, a warp per 512-byte
 //     row piece) into a row-major ring stage; the copies signal the stage's mbarrier themselves
 //     (cp.async.mbarrier.arrive.noinc), so the whole 8-stage ring stays in flight.
-//   * B = slab chunk (64 rows x 32 columns), K-major SWIZZLE_128B, pre-swizzled at operator build
-//     time (hi | lo images, 16 KB), one TMA bulk copy per chunk, reused by the chunk's 4 items
-//     (2 time steps x 2 feature chunks at F = 256).
+//   * B = slab chunk (64 rows x 32 columns), K-major SWIZZLE_128B, stored pre-swizzled as fp32 (8 KB)
+//     at operator build time: one TMA bulk copy per chunk, split into tf32 hi | lo images by a
+//     dedicated warp, reused by the chunk's 4 items (2 time steps x 2 feature chunks at F = 256).
 //   * precision: 3xTF32.  hi = x with the low 13 mantissa bits cleared, lo = x - hi, and
 //     D += Ah*Bh + Al*Bh + Ah*Bl with fp32 accumulation in TMEM.  The tensor core ignores the low
 //     13 bits of a tf32 operand, so the gathered fp32 rows are used as Ah as they are and only Al
@@ -24,9 +24,10 @@
 //     build time.  Measured 1e-6..3e-6 relative (tools/microbench/umma_tf32_test.cu).
 //   * TMEM: 4 accumulators of [128 lanes x 64 columns] + 4 A tiles of (32 hi + 32 lo) columns =
 //     all 512 columns, one persistent CTA per SM.
-//   * 22 warps, all hand-offs through mbarriers: 4 producer warps (one per accumulator index), 16
+//   * 23 warps, all hand-offs through mbarriers: 4 producer warps (one per accumulator index), 16
 //     "split" warps (4 groups x TMEM lane quarter: ring stage -> hi | lo -> tcgen05.st, and the
-//     accumulator drain), 2 MMA-issuing warps (one elected thread each, 12 tcgen05.mma per item).
+//     accumulator drain), 2 MMA-issuing warps (one elected thread each, 12 tcgen05.mma per item),
+//     1 slab warp.
 //     Lessons that shaped it (profiles/r1_trace_tc.txt): a lone warp issues dependent instructions
 //     ~5 cycles apart, so every role's per-item loop must be a few dozen instructions (barrier
 //     addresses precomputed, nothing recomputed per item, no trace code compiled in); `lane == 0`
@@ -59,7 +60,8 @@ constexpr int kTcStageBytes = kTcKC * 128 * 4;      // 16 KB: 32 rows x 128 feat
 constexpr int kTcBBytes = 2 * kTcR * kTcKC * 4;     // 16 KB: hi + lo image of one chunk
 constexpr int kTcBBufs = 3;         // slab-image buffers (3: a producer may only wait on MMAs >= 3 chunks old,
                                     // anything newer can depend on items it has not signalled yet)
-constexpr size_t kTcSmem = (size_t)kTcStages * kTcStageBytes + kTcBBufs * kTcBBytes + 1024;
+constexpr int kTcBRawBytes = kTcR * kTcKC * 4;      // 8 KB: the chunk's fp32 slab image as stored in the operator
+constexpr size_t kTcSmem = (size_t)kTcStages * kTcStageBytes + kTcBBufs * (kTcBBytes + kTcBRawBytes) + 1024;
 // TMEM columns: [0, 256) four fp32 accumulators of 64 columns, [256, 512) four A tiles of
 // (32 hi + 32 lo) columns
 constexpr int kTcTmemCols = 512;
@@ -174,7 +176,7 @@ __device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volati
                     "r"(arr[24]), "r"(arr[25]), "r"(arr[26]), "r"(arr[27]), "r"(arr[28]), "r"(arr[29]),        \
                     "r"(arr[30]), "r"(arr[31]) : "memory")
 
-// Warp roles (22 warps): warps 0-15 "split" in four groups of four (group = accumulator index,
+// Warp roles (23 warps; warp 22 splits the slab images): warps 0-15 "split" in four groups of four (group = accumulator index,
 // warp & 3 = the TMEM lane quarter the warp may touch), warps 16-19 "producer" (cp.async gathers;
 // producer 0 also fetches the slab images), warps 20-21 issue the MMAs (items a = q mod 2).
 // An item is (chunk c, accumulator a); i = 4c + a; ring stage s = i % 8; A tile = a.
@@ -182,7 +184,8 @@ __device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volati
 //            empty[s] split -> producers  : the split group has copied stage s into TMEM
 //            ready[a] split -> MMA        : A tile a (hi | lo) is in TMEM
 //            afree[a] MMA (tcgen05.commit) -> split : the MMAs reading A tile a have completed
-//            bfull[c%3] producer 0 (TMA bytes) -> MMA : the chunk's slab images have landed
+//            braw[c%3]  producer 0 (TMA bytes) -> slab warp : the chunk's fp32 slab image has landed
+//            bfull[c%3] slab warp -> MMA : the chunk's hi | lo slab images are written
 //            bfree[c%3] MMA (tcgen05.commit, both issuers) -> producer 0 : slab buffer may be overwritten
 //            done     MMA (both issuers) -> split : the work item's accumulators are complete
 //            accfree[a] split (16 warps) -> MMA : accumulator a has been read out
@@ -191,7 +194,7 @@ __device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volati
 // them; the 12 MMAs of an item then fetch only the 2 KB slab operand from shared memory each, so
 // shared-memory bandwidth (the limit of the all-in-smem version: 120 KB per item) drops to 56 KB.
 template <int NFC, bool HALO, int kTcProducerWarps>
-__global__ void __launch_bounds__((kTcSplitWarps + kTcProducerWarps + kTcIssuers) * 32, 1)
+__global__ void __launch_bounds__((kTcSplitWarps + kTcProducerWarps + kTcIssuers + 1) * 32, 1)
 spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ grp_rows,
                    const int32_t* __restrict__ cols, const float* __restrict__ bimg,
                    int n_groups, int n_work, int group_major, int gather_policy,
@@ -202,7 +205,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
     constexpr int TB = kTcAcc / NFC;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-window address
-    __shared__ uint64_t full[kTcStages], empty[kTcStages], ready[kTcABufs], afree[kTcABufs], bfree[kTcBBufs], bfull[kTcBBufs];
+    __shared__ uint64_t full[kTcStages], empty[kTcStages], ready[kTcABufs], afree[kTcABufs], bfree[kTcBBufs], bfull[kTcBBufs], braw[kTcBBufs];
     __shared__ uint64_t done, accfree[kTcAcc];
     __shared__ uint32_t tmem_base_s;
     __shared__ volatile int abort_s;
@@ -231,7 +234,8 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         }
         for (int b = 0; b < kTcBBufs; ++b) {
             mbar_init(&bfree[b], kTcIssuers);
-            mbar_init(&bfull[b], 1);           // producer 0's arrive.expect_tx; the bulk copy completes the bytes
+            mbar_init(&bfull[b], 1);           // the slab warp: hi | lo images written
+            mbar_init(&braw[b], 1);            // producer 0's arrive.expect_tx; the bulk copy completes the bytes
         }
         mbar_init(&done, kTcIssuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -245,7 +249,8 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
-    constexpr uint32_t kBOff = kTcStages * kTcStageBytes;               // slab images after the ring
+    constexpr uint32_t kBOff = kTcStages * kTcStageBytes;               // slab images (hi | lo) after the ring
+    constexpr uint32_t kBRawOff = kBOff + kTcBBufs * kTcBBytes;         // then the raw fp32 slab images
     // Work order of this (persistent) CTA, s-th work item:
     //   group_major == 0 (default): w = blockIdx.x + s * gridDim.x, (time block, group) =
     //     (w / n_groups, w % n_groups): all CTAs sweep the groups of one time block together, so
@@ -332,13 +337,13 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                                  :: "r"(dst + j * 512), "l"(p), "l"(pol_keep));
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(fbar) : "memory");
-                if (pw == 0 && lane == 0) {   // the chunk's slab images (hi | lo), reused by its 4 items: bfull[bi]
-                    const uint32_t bbar = smem_u32(&bfull[bi]);
+                if (pw == 0 && lane == 0) {   // the chunk's fp32 slab image -> raw buffer bi (the slab warp splits it)
+                    const uint32_t bbar = smem_u32(&braw[bi]);
                     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
-                                 :: "r"(bbar), "r"(kTcBBytes) : "memory");
+                                 :: "r"(bbar), "r"(kTcBRawBytes) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                                 :: "r"(smem_base + kBOff + bi * kTcBBytes), "l"(bimg + (size_t)(c_beg + c) * (kTcBBytes / 4)),
-                                    "r"(kTcBBytes), "r"(bbar), "l"(pol_stream) : "memory");
+                                 :: "r"(smem_base + kBRawOff + bi * kTcBRawBytes), "l"(bimg + (size_t)(c_beg + c) * (kTcBRawBytes / 4)),
+                                    "r"(kTcBRawBytes), "r"(bbar), "l"(pol_stream) : "memory");
                 }
                 if (++bi == kTcBBufs) { bi = 0; ++bph; }
                 __syncwarp();
@@ -457,6 +462,46 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                 }
             }
             if (n_chunks > 0) ++wn;
+        }
+    } else if (warp == kTcSplitWarps + kTcProducerWarps + kTcIssuers) {
+        // ================= slab warp: fp32 slab image -> tf32 hi | lo images ======================
+        // The operator stores each chunk's [64 rows x 32 columns] slab once, as fp32 in the K-major
+        // SWIZZLE_128B layout (8 KB); splitting it here instead of at build time halves the slab
+        // stream (17% of the hop's L2 traffic, 37% of its DRAM traffic).  Element-wise, so the
+        // layout is untouched: lane l handles the float4 pieces l, l + 32, ...
+        int bi = 0, bph = 0;
+        bool ok = true;
+        for (int ws = 0; ok; ++ws) {
+            int g, t_begin_unused;
+            if (!work_item(ws, g, t_begin_unused)) break;
+            const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
+#pragma unroll 1
+            for (int c = 0; c < n_chunks && ok; ++c) {
+                // raw image landed; the previous user of image buffer bi is done (producer 0 waited
+                // for bfree[bi] before it requested this copy)
+                if (!warp_wait(&braw[bi], bph & 1, &abort_s, err, lane)) { ok = false; break; }
+                const uint32_t rawp = smem_base + kBRawOff + bi * kTcBRawBytes + lane * 16;
+                const uint32_t img = smem_base + kBOff + bi * kTcBBytes + lane * 16;
+#pragma unroll 4
+                for (int j = 0; j < kTcBRawBytes / 512; ++j) {
+                    float4 w;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(rawp + j * 512));
+                    float4 h;
+                    h.x = __uint_as_float(__float_as_uint(w.x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(w.y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(w.z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(w.w) & 0xffffe000u);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
+                                 :: "r"(img + j * 512), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
+                                 :: "r"(img + kTcBRawBytes + j * 512), "f"(w.x - h.x), "f"(w.y - h.y), "f"(w.z - h.z), "f"(w.w - h.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> tensor-core reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bfull[bi]);
+                if (++bi == kTcBBufs) { bi = 0; ++bph; }
+            }
         }
     } else {
         // ================= MMA issuers: two warps, ONE elected thread each runs the whole loop ===
@@ -586,7 +631,7 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
     do {                                                                                               \
         SGP_CUDA(cudaFuncSetAttribute(spmm_rbu_tc_kernel<NFC_, HALO_, PW_>,                            \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));     \
-        spmm_rbu_tc_kernel<NFC_, HALO_, PW_><<<grid, (kTcSplitWarps + PW_ + kTcIssuers) * 32, kTcSmem, as_stream(stream)>>>( \
+        spmm_rbu_tc_kernel<NFC_, HALO_, PW_><<<grid, (kTcSplitWarps + PW_ + kTcIssuers + 1) * 32, kTcSmem, as_stream(stream)>>>( \
             chunk_ptr, grp_rows, cols, bimg, n_groups, n_work, group_major, gather_policy, src, src_t_stride, s_nb, src2, \
             src2_t_stride, s2_nb, n_split, dst, dst_t_stride, dst_n_stride, Tc, err_flag, trace_ptr);  \
     } while (0)

@@ -243,7 +243,7 @@ class TcOp:
     chunk_ptr: torch.Tensor      # [n_groups+1] int32
     grp_rows: torch.Tensor       # [n_groups, 64] int32
     cols: torch.Tensor           # [total_chunks*32] int32
-    bimg: torch.Tensor           # [total_chunks, 2, 2048] float32
+    bimg: torch.Tensor           # [total_chunks, 2048] float32 (pre-swizzled slab images)
     n_groups: int
     fill: float
     err: torch.Tensor            # device int32 flag
@@ -255,7 +255,8 @@ TC_R, TC_KC = 64, 32
 def tc_build(csr: Csr, grp_rows_h: Optional[np.ndarray] = None, n_cols: Optional[int] = None) -> TcOp:
     """Build the tcgen05 operator format from a CSR: 64-row locality groups, per group the sorted
     union of columns padded to chunks of 32, and per chunk the [64 x 32] slab of values split into
-    tf32 hi / lo images laid out exactly as the kernel's K-major SWIZZLE_128B shared-memory tile."""
+    an fp32 image laid out exactly as the kernel's K-major SWIZZLE_128B shared-memory tile (the kernel splits it
+    into tf32 hi / lo)."""
     dev = csr.rowptr.device
     N, R, KC = csr.num_nodes, TC_R, TC_KC
     if grp_rows_h is None:
@@ -296,9 +297,7 @@ def tc_build(csr: Csr, grp_rows_h: Optional[np.ndarray] = None, n_cols: Optional
     off = (s_e >> 3) * 256 + (s_e & 7) * 32 + (((k_e >> 2) ^ (s_e & 7)) << 2) + (k_e & 3)   # in floats
     img = torch.zeros(max(total_chunks, 1) * R * KC, dtype=torch.float32, device=dev)
     img.index_put_((chunk_e * (R * KC) + off,), csr.val, accumulate=True)
-    hi = (img.view(torch.int32) & -8192).view(torch.float32)          # clear the low 13 mantissa bits
-    lo = img - hi
-    bimg = torch.stack([hi.view(-1, R * KC), lo.view(-1, R * KC)], dim=1).contiguous()
+    bimg = img.view(-1, R * KC)          # fp32; the kernel splits it into tf32 hi / lo images
     fill = csr.nnz / max(int(cnt.sum()) * R, 1)
     return TcOp(chunk_ptr.to(torch.int32), grp_rows.contiguous(), cols, bimg, n_groups, fill,
                 torch.zeros(1, dtype=torch.int32, device=dev))
