@@ -69,22 +69,6 @@ constexpr int kTcAOff = kTcAcc * kTcR;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)layout_type << 61;       // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
-    return d;
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-
 // L2 eviction policies: slab images and the hop's output stream through L2 once (evict_first) so
 // that they do not push out the gathered panel rows, which neighbouring groups re-read (the
 // cross-ring reuse distance of the breadth-first group order is about one wave of CTAs).
@@ -113,32 +97,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 :: "r"(smem_u32(bar)) : "memory");
-}
-
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(smem_u32(bar)) : "memory");
-}
-
-// arrive on `bar` once all cp.async issued so far by this thread have landed (count pre-accounted)
-__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-// producer side of a byte-counted barrier: one arrival + the bytes the bulk copies will deliver
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
-                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA bulk copy global -> shared (no tensor map), completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
 // Bounded warp-wide wait (all 32 lanes poll the same word: one broadcast shared-memory access per
@@ -166,16 +130,6 @@ __device__ __forceinline__ bool warp_wait(uint64_t* bar, uint32_t parity, volati
                  :: "r"(addr), "r"(arr[0]), "r"(arr[1]), "r"(arr[2]), "r"(arr[3]), "r"(arr[4]), "r"(arr[5]),  \
                     "r"(arr[6]), "r"(arr[7]), "r"(arr[8]), "r"(arr[9]), "r"(arr[10]), "r"(arr[11]),            \
                     "r"(arr[12]), "r"(arr[13]), "r"(arr[14]), "r"(arr[15]) : "memory")
-#define SGP_TMEM_ST32(addr, arr)                                                                   \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,"  \
-                 "%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"       \
-                 :: "r"(addr), "r"(arr[0]), "r"(arr[1]), "r"(arr[2]), "r"(arr[3]), "r"(arr[4]), "r"(arr[5]),  \
-                    "r"(arr[6]), "r"(arr[7]), "r"(arr[8]), "r"(arr[9]), "r"(arr[10]), "r"(arr[11]),            \
-                    "r"(arr[12]), "r"(arr[13]), "r"(arr[14]), "r"(arr[15]), "r"(arr[16]), "r"(arr[17]),        \
-                    "r"(arr[18]), "r"(arr[19]), "r"(arr[20]), "r"(arr[21]), "r"(arr[22]), "r"(arr[23]),        \
-                    "r"(arr[24]), "r"(arr[25]), "r"(arr[26]), "r"(arr[27]), "r"(arr[28]), "r"(arr[29]),        \
-                    "r"(arr[30]), "r"(arr[31]) : "memory")
-
 // Warp roles (23 warps; warp 22 splits the slab images): warps 0-15 "split" in four groups of four (group = accumulator index,
 // warp & 3 = the TMEM lane quarter the warp may touch), warps 16-19 "producer" (cp.async gathers;
 // producer 0 also fetches the slab images), warps 20-21 issue the MMAs (items a = q mod 2).
