@@ -352,6 +352,8 @@ def sgp_encoder(x, edge_index, edge_weight, layers: Sequence[dict], activation: 
                 dtype=torch.float32) -> np.ndarray:
     """lib/nn/encoders/sgp_encoder.py:45-51: reservoir over [T,N,Fin], then the spatial encoder."""
     h = reservoir_states(x, layers, activation, dtype=dtype).numpy()
+    if impl == "c":
+        h = h.astype(np.float32, copy=False)       # the C SpMM is float32 (a float64 recurrence is rounded once)
     return spatial_encoder(h, edge_index, edge_weight, receptive_field, bidirectional,
                            undirected, global_attr, add_self_loops, impl=impl)
 
