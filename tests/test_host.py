@@ -195,3 +195,24 @@ def test_group_rows_has_no_scattered_leftover_groups():
     unions = np.array([len(np.unique(np.concatenate([col[rowptr[r]:rowptr[r + 1]] for r in gr[gr >= 0]])))
                        for gr in g])
     assert unions.max() <= 2.5 * np.median(unions), (unions.max(), np.median(unions))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with
+    the contract's keys, the oracle port as cpu_baseline, no GPU work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
+                          "--workload", "c1_metr_la", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["value"] > 0 and "workload" in line["config"]
