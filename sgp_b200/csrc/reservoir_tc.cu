@@ -161,8 +161,14 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * 128;
     // optional per-step timestamps of CTA 7 (tools/trace_rt.py); trace == nullptr in production
+    // (compiled in only with -DSGP_RT_TRACE_ON: the MMA warp's loop is latency-bound, every stamp costs)
+#ifdef SGP_RT_TRACE_ON
     const bool tr = trace && blockIdx.x == 7;
 #define SGP_RT_TRACE(role, t_, v) do { if (tr && lane == 0 && (t_) < 64) trace[(role) * 64 + (t_)] = (v); } while (0)
+#else
+    constexpr bool tr = false;
+#define SGP_RT_TRACE(role, t_, v) do { } while (0)
+#endif
 
     if (tid == 0) {
         abort_s = 0;

@@ -1,4 +1,7 @@
-"""Per-step timestamps of one CTA of the tensor-core reservoir scan (SGP_B200_RT_TRACE)."""
+"""Per-step timestamps of one CTA of the tensor-core reservoir scan (SGP_B200_RT_TRACE).
+Needs a library built with the stamps compiled in:
+    python tools/build_variants.py rttrace=-DSGP_RT_TRACE_ON
+    SGP_B200_SO=sgp_b200/variants/libsgp_b200_rttrace.so python tools/trace_rt.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
