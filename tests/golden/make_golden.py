@@ -11,7 +11,7 @@ names it imports from the rest of the reference:
   * tsl.nn.utils.get_functional_activation   (semantics of tsl/nn/utils/utils.py:34-44)
   * lib.utils.self_normalizing_activation    (semantics of lib/utils.py:50-51)
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]
 """
 import importlib.util
 import os
@@ -68,12 +68,20 @@ CASES = {
     "tanh_h64_la": (16, 48, 23, 3, dict(hidden_size=64, num_layers=2, leaking_rate=0.9,
                                          spectral_radius=0.9, density=0.7, activation="tanh",
                                          alpha_decay=True)),
+    # the shapes the tensor-core scan covers (H = 128 / 256, one layer, more than one 128-node tile)
+    "tanh_h128_tc": (17, 30, 150, 3, dict(hidden_size=128, num_layers=1, leaking_rate=0.9,
+                                           spectral_radius=0.9, density=0.7, activation="tanh")),
+    "tanh_h256_tc": (18, 24, 70, 1, dict(hidden_size=256, num_layers=1, leaking_rate=0.9,
+                                          spectral_radius=0.9, density=0.7, activation="tanh")),
 }
 
 
 def main():
     ref = load_reference_reservoir()
+    only = set(sys.argv[1:])           # optional: regenerate just the named cases
     for name, (seed, T, N, Fin, kw) in CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(seed)
         res = ref.Reservoir(input_size=Fin, **kw)
         g = torch.Generator().manual_seed(seed + 1000)

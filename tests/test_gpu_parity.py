@@ -120,6 +120,15 @@ def test_scan_tensor_core_vs_oracle(H, N, Fin, act):
     np.testing.assert_array_equal(st2, st)
 
 
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.endswith("_tc")])
+def test_scan_tensor_core_vs_reference_golden(name):
+    """The tcgen05 scan against outputs of the UNMODIFIED reference reservoir (tests/golden/make_golden.py)."""
+    g = load_golden(name)
+    assert g["kwargs"]["hidden_size"] in (128, 256) and len(g["layers"]) == 1
+    y, _ = run_scan_tc(g["x"], g["layers"][0], g["kwargs"].get("activation", "tanh"))
+    assert_blocks_close(y, g["y"], g["kwargs"]["hidden_size"])
+
+
 def test_scan_tensor_core_long_recurrence():
     """1000 steps at H=256 against the float64 oracle: 3xTF32 keeps fp32-level accuracy."""
     torch.manual_seed(9)
