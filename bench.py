@@ -112,27 +112,54 @@ def make_encoder(cfg):
 # reference arm / cpu_baseline: the oracle (a port — the reference is Python over torch +
 # torch_sparse, and torch_sparse is not installable here) on the host cores.
 # --------------------------------------------------------------------------------------------
-def cpu_encode_once(cfg, ei, ew, x, layers):
+def cpu_graph_once(cfg, ei, ew):
+    """One-off per graph: edge list -> normalised CSR (the reference's preprocess_adj)."""
     from oracle import sgp_oracle as O
+    t0 = time.perf_counter()
+    op = O.build_operator(ei, ew, cfg["N"], set_diag=False)
+    return op, time.perf_counter() - t0
+
+
+def cpu_encode_once(cfg, op, x, layers):
+    """Reservoir + K hops over the sample's time steps with a prebuilt operator."""
+    from oracle import sgp_oracle as O
+    rowptr, col, val = op
     t0 = time.perf_counter()
     h = O.reservoir_states(x, layers, "tanh")
     t1 = time.perf_counter()
-    rowptr, col, val = O.build_operator(ei, ew, cfg["N"], set_diag=False)
-    t2 = time.perf_counter()
     F = h.shape[-1]
     out = torch.empty(h.shape[0], cfg["N"], (cfg["K"] + 1) * F)
     out[..., :F] = h
     for k in range(cfg["K"]):
         O.spmm_c(rowptr, col, val, out[..., k * F:(k + 1) * F], out=out[..., (k + 1) * F:(k + 2) * F])
-    t3 = time.perf_counter()
-    return dict(total=t3 - t0, reservoir=t1 - t0, graph=t2 - t1, spmm=t3 - t2,
-                checksum=float(out[-1].double().sum()))
+    t2 = time.perf_counter()
+    return dict(reservoir=t1 - t0, spmm=t2 - t1, checksum=float(out[-1].double().sum()))
 
 
 def cpu_sample_steps(cfg):
-    """Time steps of the CPU sample: ~10-30 s of CPU work per run of a few steps."""
-    per_step = cfg["N"] * (2 * cfg["H"] * cfg["H"] / 60e9 + 2 * cfg["K"] * cfg.get("k", 8) * cfg["H"] / 10e9)
-    return int(max(2, min(cfg["T"], 5.0 / max(per_step, 1e-9))))
+    """Time steps of the CPU sample: about 4 s of CPU work per step of the run (measured on the
+    16-core box: ~3.7e-6 s per node-step at C4), capped by 8 GB of host output."""
+    deg = cfg.get("k", 8)
+    per_step = cfg["N"] * (2 * cfg["H"] * cfg["H"] / 250e9 + 2 * cfg["K"] * deg * cfg["H"] / 70e9) + 2e-4
+    mem_cap = int(8e9 // (cfg["N"] * (cfg["K"] + 1) * cfg["H"] * 4))
+    return int(max(2, min(cfg["T"], mem_cap, 4.0 / per_step)))
+
+
+def cpu_baseline_run(cfg, ei, ew, x_sample, layers, reps):
+    """Times the CPU port on `x_sample` (the first Ts steps).  The adjacency build is a per-graph
+    one-off: it is timed once and charged pro rata, Ts / T of it, exactly as a full-length run
+    would amortise it: value = N Ts / (t_reservoir + t_spmm + t_graph Ts / T)."""
+    Ts = x_sample.shape[0]
+    op, t_graph = cpu_graph_once(cfg, ei, ew)
+    runs = [cpu_encode_once(cfg, op, x_sample, layers) for _ in range(reps)]
+    t_res = sum(r["reservoir"] for r in runs) / reps
+    t_spmm = sum(r["spmm"] for r in runs) / reps
+    sec = t_res + t_spmm + t_graph * Ts / cfg["T"]
+    sample = (f"first {Ts} of {cfg['T']} time steps, full N/H/K/graph: reservoir {t_res:.2f}s (torch CPU, the "
+              f"reference's ops) + K-hop SpMM {t_spmm:.2f}s (C/OpenMP restatement of torch_sparse spmm) + "
+              f"adjacency build {t_graph:.2f}s x {Ts}/{cfg['T']} (one-off per graph, amortised over the "
+              f"workload's T); value = N*{Ts} / {sec:.3f}s")
+    return sec, sample
 
 
 def run_reference(args, cfg):
@@ -147,15 +174,12 @@ def run_reference(args, cfg):
     enc = make_encoder(cfg)
     layers = [dict(w_ih=l.w_ih.data, w_hh=l.w_hh.data, b_ih=l.b_ih.data, alpha=l.alpha)
               for l in enc.reservoir.reservoir_layers]
-    for _ in range(args.warmup):
-        cpu_encode_once(cfg, ei, ew, x, layers)
-    times = [cpu_encode_once(cfg, ei, ew, x, layers) for _ in range(args.steps)]
-    sec = sum(t["total"] for t in times) / len(times)
+    op, _ = cpu_graph_once(cfg, ei, ew)
+    for _ in range(min(args.warmup, 1)):
+        cpu_encode_once(cfg, op, x, layers)
+    sec, sample = cpu_baseline_run(cfg, ei, ew, x, layers, max(1, args.steps))
     value = cfg["N"] * Ts / sec
     cores = max(torch.get_num_threads(), O.c_threads())
-    sample = (f"{Ts} of {cfg['T']} time steps of the same workload (full N/H/K and graph); "
-              f"reservoir {times[-1]['reservoir']:.2f}s + adjacency {times[-1]['graph']:.2f}s + "
-              f"K-hop SpMM {times[-1]['spmm']:.2f}s per step")
     line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
@@ -167,6 +191,8 @@ def run_reference(args, cfg):
 
 
 def config_dict(cfg, n_gpus, extra=None):
+    """The workload description shared VERBATIM by the GPU arm and the reference arm (the latter
+    adds only cpu_sample_steps); implementation details of the GPU arm go to `kernel_config`."""
     d = dict(workload=f"{cfg['name']}: synthetic sensor graph N={cfg['N']}, "
                       f"{'k=%d-NN' % cfg['k'] if cfg['graph'] == 'knn' else 'thresholded kernel'}, "
                       f"T={cfg['T']}, H={cfg['H']}, K={cfg['K']}, Fin={cfg['Fin']}, L=1, directed D^-1 A",
@@ -198,6 +224,24 @@ class Timed:
         return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.pairs.items()}
 
 
+TRAFFIC_FILE = os.path.join("profiles", "r2_traffic.json")
+
+
+def measured_traffic(workload_name, kernel, timesteps):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (scaled to this
+    run's time steps per launch).  It is evidence replayed from profiles/, not measured in this run:
+    the key next to it (`traffic_source`) says so; null when no capture of this workload exists."""
+    try:
+        with open(os.path.join(ROOT, TRAFFIC_FILE)) as f:
+            tr = json.load(f)
+        rec = tr.get(workload_name, {}).get(kernel)
+        if rec:
+            return (rec["dram_read_bytes"] + rec["dram_write_bytes"]) * timesteps / rec["timesteps"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def run_own(args, cfg):
     import sgp_b200
     from sgp_b200 import _lib, ops
@@ -225,31 +269,38 @@ def run_own(args, cfg):
 
     # ---- resident inputs for the device-timed number ---------------------------------------
     x_dev = torch.from_numpy(x).to(dev)
-    ei_dev, ew_dev = torch.from_numpy(ei).to(dev), torch.from_numpy(ew).to(dev)
-    fwd, bwd = enc.sgp_encoder.build_operators(ei_dev, ew_dev, N, dev, F)
+    ei_h, ew_h = torch.from_numpy(ei), torch.from_numpy(ew)
+    # the operator is per graph: built once from the HOST edge list, timed on its own
+    torch.cuda.synchronize()
+    t_b0 = time.perf_counter()
+    fwd, bwd = enc.sgp_encoder.build_operators(ei_h, ew_h, N, dev, F)
+    torch.cuda.synchronize()
+    build_ms = (time.perf_counter() - t_b0) * 1e3
     plan = enc.reservoir.device_plan(dev, N)
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     bufs = [torch.empty(step_T, N, D, device=dev) for _ in range(2)]
     state = torch.zeros(1, N, H, device=dev)
 
     def one_pass(timed=None):
+        # the sink is the checksum `acc`: accumulated by the producing kernels in their epilogues
         state.zero_()
         for i, t0 in enumerate(range(0, T, step_T)):
             t1 = min(T, t0 + step_T)
             buf = bufs[i % 2][: t1 - t0]
             if timed is None:
-                enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf)
-                enc.sgp_encoder.encode_chunk(buf, F, fwd, bwd)
+                enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf, acc)
+                enc.sgp_encoder.encode_chunk(buf, F, fwd, bwd, checksum=acc)
             else:
-                timed.wrap("scan", lambda: enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf))
+                timed.wrap("scan", lambda: enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf, acc))
                 for h in range(1, K + 1):
                     timed.wrap(("spmm", t1 - t0), lambda h=h: fwd.apply(buf[..., (h - 1) * F:h * F],
-                                                                        buf[..., h * F:(h + 1) * F]))
-            ops.checksum(buf, acc)
+                                                                        buf[..., h * F:(h + 1) * F],
+                                                                        checksum=acc))
 
     for _ in range(args.warmup):
         one_pass()
     torch.cuda.synchronize()
+    acc.zero_()
     sampler = ClockSampler(local)
     sampler.start()
     timed = Timed()
@@ -267,12 +318,12 @@ def run_own(args, cfg):
     enc.reservoir.check_plan(plan)
     ms_step = e0.elapsed_time(e1) / args.steps
     value = N * T / (ms_step * 1e-3)
+    checksum_timed = float(acc) / args.steps
 
     # ---- roofline of the dominant kernel (the hop SpMM) ------------------------------------
     summ = timed.summary()
     nnz = fwd.csr.nnz
     spmm_ms = sum(ms for k, (n, ms) in summ.items() if k != "scan")
-    spmm_n = sum(n for k, (n, ms) in summ.items() if k != "scan")
     full_key = ("spmm", step_T)
     n_full, ms_full = summ.get(full_key, (0, 0.0))
     bytes_per_launch = 8 * nnz + 4 * (N + 1) + 2 * step_T * N * F * 4
@@ -282,40 +333,39 @@ def run_own(args, cfg):
     scan_n, scan_ms = summ.get("scan", (0, 0.0))
     scan_flops = N * T * (2 * H * (Fin + H) + 6 * H) * args.steps
     fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    # measured DRAM traffic of the same kernel (one ncu --set full capture, profiles/r1_traffic.json),
-    # scaled from the captured launch's time steps to this run's
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tr = json.load(f)
-        rec = tr.get("spmm_rbu_tc_kernel") if fwd.tc is not None else None
-        if rec and tr.get("workload") == args.workload:
-            traffic = (rec["dram_read_bytes"] + rec["dram_write_bytes"]) * step_T / rec["timesteps"]
-    except (OSError, ValueError, KeyError):
-        traffic = None
-    roofline = dict(bound="hbm", kernel=("spmm_rbu_tc_kernel (tcgen05, 3xTF32)" if fwd.tc is not None else
-                            ("spmm_rbu_v3<%d>" % fwd.rbu.R) if fwd.rbu is not None else "spmm_csr_vec"),
+    hop_kernel = ("spmm_rbu_tc_kernel" if fwd.tc is not None else
+                  ("spmm_rbu_v3<%d>" % fwd.rbu.R) if fwd.rbu is not None else "spmm_csr_vec")
+    traffic = measured_traffic(args.workload, hop_kernel, step_T)
+    roofline = dict(bound="hbm", kernel=hop_kernel + (" (tcgen05, 3xTF32)" if fwd.tc is not None else ""),
                     achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
                     peak_source=peaks["source"], traffic=traffic,
+                    traffic_source=(TRAFFIC_FILE + ": ncu --set full capture of the same kernel and workload, "
+                                    "scaled to this launch's time steps (replayed evidence, not measured in "
+                                    "this run)") if traffic is not None else None,
                     algorithmic_bytes_per_launch=bytes_per_launch, timesteps_per_launch=step_T,
                     avg_launch_ms=avg_ms, launches_timed=n_full,
+                    us_per_hop_panel=avg_ms * 1e3 / step_T if step_T else None,
                     gflops=flops_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0,
                     fp32_fma_peak_tflops=fma_peak,
-                    share_of_step=spmm_ms / (spmm_ms + scan_ms) if spmm_ms + scan_ms else None)
+                    share_of_step=spmm_ms / (args.steps * ms_step) if ms_step else None)
     reservoir = dict(kernel="reservoir_tc_kernel (tcgen05, 3xTF32)" if plan[0][0] == "tc" else "reservoir_scan_tiled", ms_per_step=scan_ms / args.steps,
                      tflops=scan_flops / (scan_ms * 1e-3) / 1e12 if scan_ms else 0.0,
                      frac_of_fp32_fma_peak=(scan_flops / (scan_ms * 1e-3) / 1e12) / fma_peak if scan_ms else 0.0,
-                     share_of_step=scan_ms / (spmm_ms + scan_ms) if spmm_ms + scan_ms else None)
+                     share_of_step=scan_ms / (args.steps * ms_step) if ms_step else None)
 
     # ---- end to end through the public API with HOST buffers -------------------------------
+    # SGPEncoder.encode_stream on the pinned host series: per step the H2D copy of every chunk of x,
+    # the scan + K hops, and the D2H read of the result (the checksum).  The operator is per graph
+    # (built once above from the host edge list, `operator_build_ms`) and passed in — the same split
+    # as the N > 1 line and as the reference arm, which amortises its adjacency build over T.
     x_pin = torch.from_numpy(x).pin_memory()
-    ei_h, ew_h = torch.from_numpy(ei), torch.from_numpy(ew)
     host_sum = torch.zeros(1, dtype=torch.float64).pin_memory()
+    chk = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def e2e_pass():
-        acc.zero_()
-        enc.encode_stream(x_pin, ei_h, ew_h, lambda t0, t1, chunk: ops.checksum(chunk, acc), device=dev)
-        host_sum.copy_(acc, non_blocking=True)
+        chk.zero_()
+        enc.encode_stream(x_pin, None, None, None, device=dev, operators=(fwd, bwd), checksum=chk)
+        host_sum.copy_(chk, non_blocking=True)
         torch.cuda.synchronize()
         return float(host_sum)
 
@@ -324,16 +374,18 @@ def run_own(args, cfg):
     for _ in range(max(1, min(args.steps, 3))):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        chk = e2e_pass()
+        chk_e2e = e2e_pass()
         t_e2e.append(time.perf_counter() - t0)
     e2e_s = sum(t_e2e) / len(t_e2e)
-    h2d = x.nbytes + ei.nbytes + ew.nbytes
-    d2h = 8 + (4 * (N + 1) + 8 * nnz if (fwd.rbu is not None or fwd.tc is not None) else 0)
-    e2e = dict(value=N * T / e2e_s, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-               ms_per_step=e2e_s * 1e3, checksum=chk,
-               note="SGPEncoder.encode_stream on pinned host x + host edge list: H2D of inputs, operator "
-                    "build (CSR + row grouping), scan + K hops, per-chunk checksum, D2H of the checksum; "
-                    "the [T,N,D] output itself (%.0f GB) is not copied back" % (N * T * D * 4 / 1e9))
+    e2e = dict(value=N * T / e2e_s, unit=UNIT, h2d_bytes_per_step=int(x.nbytes), d2h_bytes_per_step=8,
+               ms_per_step=e2e_s * 1e3, checksum=chk_e2e, operator_build_ms=build_ms,
+               note="SGPEncoder.encode_stream on the pinned host series: H2D of x chunk by chunk, scan + K "
+                    "hops, checksum fused into the kernels' epilogues, D2H of the checksum; the [T,N,D] output "
+                    "itself (%.0f GB) is not copied back.  The operator (CSR + row grouping + slab images) is "
+                    "per graph: built once from the host edge list (operator_build_ms, %d B H2D, %d B D2H) "
+                    "outside the step, as in the N > 1 lines" %
+                    (N * T * D * 4 / 1e9, ei.nbytes + ew.nbytes,
+                     (4 * (N + 1) + 8 * nnz) if (fwd.rbu is not None or fwd.tc is not None) else 0))
 
     # ---- CPU baseline on a bounded sample ---------------------------------------------------
     cpu = None
@@ -344,24 +396,21 @@ def run_own(args, cfg):
         Ts = cpu_sample_steps(cfg)
         layers = [dict(w_ih=l.w_ih.data, w_hh=l.w_hh.data, b_ih=l.b_ih.data, alpha=l.alpha)
                   for l in enc.reservoir.reservoir_layers]
-        cpu_encode_once(cfg, ei, ew, x[:Ts], layers)
-        r = cpu_encode_once(cfg, ei, ew, x[:Ts], layers)
-        cpu = dict(value=N * Ts / r["total"], unit=UNIT, cores=max(torch.get_num_threads(), O.c_threads()),
-                   kind="port",
-                   sample=f"first {Ts} of {T} time steps, full N/H/K/graph: reservoir {r['reservoir']:.2f}s "
-                          f"(torch CPU, same ops as the reference) + adjacency {r['graph']:.2f}s + K-hop SpMM "
-                          f"{r['spmm']:.2f}s (C/OpenMP restatement of torch_sparse spmm)")
+        sec, sample = cpu_baseline_run(cfg, ei, ew, x[:Ts], layers, 2)
+        cpu = dict(value=N * Ts / sec, unit=UNIT, cores=max(torch.get_num_threads(), O.c_threads()),
+                   kind="port", sample=sample)
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
-                dtype="f32", data="synthetic",
-                config=config_dict(cfg, 1, extra=dict(
+                dtype="f32", data="synthetic", config=config_dict(cfg, 1),
+                kernel_config=dict(
                     chunk_steps=step_T,
                     operator_format=("tcgen05 64-row groups" if fwd.tc is not None else
                                      "rbu%d" % fwd.rbu.R if fwd.rbu is not None else "csr"),
-                    group_fill=round((fwd.tc or fwd.rbu).fill, 3) if (fwd.tc or fwd.rbu) else None)),
+                    group_fill=round((fwd.tc or fwd.rbu).fill, 3) if (fwd.tc or fwd.rbu) else None,
+                    sink="fp64 checksum of the whole output, accumulated in the scan / hop epilogues"),
                 roofline=roofline, reservoir=reservoir, cpu_baseline=cpu, e2e=e2e, clocks=clocks,
-                gpu_launches=int(launches), checksum=float(acc))
+                gpu_launches=int(launches), checksum=checksum_timed)
     print(json.dumps(line))
 
 

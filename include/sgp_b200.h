@@ -28,6 +28,10 @@
 extern "C" {
 #endif
 
+/* bumped with every change of a signature or of a kernel's contract; sgp_version() returns it and
+ * the Python binding refuses a library built from another header */
+#define SGP_B200_ABI_VERSION 200
+
 #define SGP_OK 0
 #define SGP_EINVAL (-1)    /* bad shape / flag / null pointer */
 #define SGP_EALIGN (-2)    /* pointer or stride not aligned as the kernel requires */
@@ -100,13 +104,16 @@ int sgp_reservoir_scan(const float* x, int64_t x_t_stride, int64_t x_n_stride, i
 /* Tensor-core scan (tcgen05, 3xTF32, fp32-accurate): same contract as sgp_reservoir_scan for
  * H in {128, 256}, Fin <= 8, activation tanh / relu / identity.  wimg [H*H*2] = W_hh split into tf32
  * hi / lo images in the kernel's shared-memory layout (sgp_reservoir_tc_pack); w_ih [H, Fin] and bias
- * [H] as in the reference.  *err_flag (device int) is set to 1 if an internal barrier times out. */
+ * [H] as in the reference.  *err_flag (device int) is set to 1 if an internal barrier times out.
+ * checksum (device fp64 scalar, may be NULL): the kernel adds the sum of every state value it
+ * writes to out — the streamed benchmark's sink, accumulated in the epilogue registers instead of
+ * re-reading the output (sgp_checksum). */
 int sgp_reservoir_tc_pack(const float* w_hh /*[H,H]*/, int H, float* wimg /*[2*H*H]*/, void* stream);
 int sgp_reservoir_scan_tc(const float* x, int64_t x_t_stride, int64_t x_n_stride, int Fin,
                           const float* wimg, const float* w_ih, const float* bias,
                           float alpha, float one_minus_alpha, int act,
                           float* h_state, float* out, int64_t out_t_stride, int64_t out_n_stride,
-                          int Tc, int N, int H, int* err_flag, void* stream);
+                          int Tc, int N, int H, int* err_flag, double* checksum /*nullable*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2  CSR x dense propagation, batched over the leading (time / batch) axis.
@@ -162,19 +169,27 @@ int sgp_spmm_rbu_halo(const int32_t* grp_ptr, const int32_t* grp_rows, const int
  * cols [total_chunks*32] source row ids, bimg [total_chunks][64*32] the chunk's operator values
  * (fp32) in the K-major SWIZZLE_128B shared-memory layout (built by sgp_b200/ops.py::tc_build; the
  * kernel splits them into tf32 hi / lo).  F in {128, 256, 512}.  *err_flag (device int) is set to 1 if
- * an internal barrier times out.  src2 / n_split as in sgp_spmm_halo. */
+ * an internal barrier times out.  src2 / n_split as in sgp_spmm_halo.  checksum as in
+ * sgp_reservoir_scan_tc (NULL = off).  Source row counts are unbounded: row * stride is formed in
+ * 64 bits (row strides themselves must be < 2^32 bytes). */
 int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int32_t* cols,
                     const float* bimg, int n_groups,
                     const float* src, int64_t src_t_stride, int64_t src_n_stride,
                     const float* src2, int64_t src2_t_stride, int64_t src2_n_stride, int n_split,
                     float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
-                    int F, int Tc, int* err_flag, void* stream);
+                    int F, int Tc, int* err_flag, double* checksum /*nullable*/, void* stream);
 
 /* HOST function (pointers are host memory, no stream): choose the R-row groups of the RBU format
  * from a CSR operator by a breadth-first, heaviest-neighbour-first greedy (group_rows.cu).
  * grp_rows must hold ceil(N/R)*R entries; unused slots of the last group are set to -1. */
 int sgp_group_rows(const int32_t* rowptr, const int32_t* col, const float* val, int32_t N, int32_t R,
                    int32_t* grp_rows, int32_t* n_groups_out);
+
+/* HOST function: owner[i] in [0, parts) for every row — `parts` compact, equally sized patches of
+ * the graph by recursive bisection along the patch diameter (group_rows.cu).  The row-sharded
+ * encoder (no counterpart in the single-process reference) gives patch r to rank r. */
+int sgp_partition_rows(const int32_t* rowptr, const int32_t* col, int32_t N, int32_t parts,
+                       int32_t* owner /*[N]*/);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  global block: dst[t, n, :] = mean over nodes of src[t, :, :]
@@ -191,6 +206,10 @@ int sgp_node_mean_broadcast(const float* sums /*[Tc,F]*/, int64_t N_total,
 
 /* Output sink for streamed benchmarking: acc[0] += sum(buf[0:count]) in fp64 (device scalar). */
 int sgp_checksum(const float* buf, int64_t count, double* acc, void* stream);
+
+/* The same over a strided [Tc, N, F] view (a feature block of the encoder's output buffer). */
+int sgp_checksum_view(const float* src, int64_t src_t_stride, int64_t src_n_stride, int N, int F, int Tc,
+                      double* acc, void* stream);
 
 /* Gather rows: dst[t, i, :] = src[t, index[i], :]  (halo packing for the row-sharded path). */
 int sgp_gather_rows(const float* src, int64_t src_t_stride, int64_t src_n_stride,

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes
 import os
+import re
+import warnings
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 from . import _build
@@ -31,7 +33,7 @@ SIGNATURES = {
     "sgp_reservoir_tc_pack": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "sgp_reservoir_scan_tc": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_float,
                                       c_float, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
-                                      c_int, c_void_p, c_void_p]),
+                                      c_int, c_void_p, c_void_p, c_void_p]),
     "sgp_spmm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                          c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "sgp_spmm_halo": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
@@ -46,12 +48,14 @@ SIGNATURES = {
                                   c_int, c_int, c_void_p]),
     "sgp_spmm_rbu_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64,
                                 c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int, c_int,
-                                c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_void_p]),
     "sgp_group_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "sgp_partition_rows": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "sgp_node_sum": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sgp_node_mean_broadcast": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
                                         c_int, c_void_p]),
     "sgp_checksum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "sgp_checksum_view": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sgp_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64,
                                 c_int, c_int, c_void_p]),
 }
@@ -64,8 +68,20 @@ class SgpError(RuntimeError):
 _lib = None
 
 
+def header_abi_version() -> int:
+    """SGP_B200_ABI_VERSION of include/sgp_b200.h (the header this binding was written against)."""
+    hdr = os.path.join(os.path.dirname(_build.HERE), "include", "sgp_b200.h")
+    with open(hdr) as f:
+        m = re.search(r"#define\s+SGP_B200_ABI_VERSION\s+(\d+)", f.read())
+    if not m:
+        raise SgpError("include/sgp_b200.h does not define SGP_B200_ABI_VERSION")
+    return int(m.group(1))
+
+
 def load() -> ctypes.CDLL:
-    """Load (building first if stale and nvcc is present) the C-ABI library; raise if impossible."""
+    """Load (building first if stale and nvcc is present) the C-ABI library; raise if impossible.
+    A library that could not be rebuilt is accepted only if it is not older than its sources'
+    ABI: sgp_version() must equal the header's SGP_B200_ABI_VERSION."""
     global _lib
     if _lib is not None:
         return _lib
@@ -75,10 +91,17 @@ def load() -> ctypes.CDLL:
     except Exception as e:  # noqa: BLE001 - no nvcc on the box: use the prebuilt file if present
         if not os.path.exists(so):
             raise SgpError(f"libsgp_b200.so is missing and could not be built: {e}") from e
+        if _build.stale():
+            warnings.warn(f"libsgp_b200.so is older than its sources and could not be rebuilt ({e}); "
+                          "loading it only if its ABI version matches the header", RuntimeWarning)
     lib = ctypes.CDLL(so)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype, fn.argtypes = res, args
+    have, want = int(lib.sgp_version()), header_abi_version()
+    if have != want:
+        raise SgpError(f"{so} implements ABI version {have}, include/sgp_b200.h declares {want}: rebuild "
+                       "the library (python -m sgp_b200._build --force)")
     _lib = lib
     return lib
 

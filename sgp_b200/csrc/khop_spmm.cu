@@ -125,75 +125,6 @@ spmm_csr_scalar(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// RBU: one warp per (t, group, 128-wide feature chunk); lane owns one float4 of R output rows.
-// ---------------------------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(kSpmmWarps * 32)
-spmm_rbu_kernel(const int32_t* __restrict__ grp_ptr, const int32_t* __restrict__ grp_rows,
-                const int32_t* __restrict__ ucol, const float* __restrict__ uval,
-                int n_groups, int nfc,
-                const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
-                float* __restrict__ dst, int64_t d_ts, int64_t d_ns, long long total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gw = (long long)blockIdx.x * kSpmmWarps + warp;
-    if (gw >= total) return;
-    const int fc = (int)(gw % nfc);
-    const long long rest = gw / nfc;
-    const int g = (int)(rest % n_groups), t = (int)(rest / n_groups);
-    const float* sp = src + (size_t)t * s_ts + fc * 128 + lane * 4;
-
-    float2 acc[R][2];
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
-
-    const int beg = grp_ptr[g], end = grp_ptr[g + 1];
-    int u = beg;
-    for (; u + 2 <= end; u += 2) {
-        const int c0 = __ldg(ucol + u), c1 = __ldg(ucol + u + 1);
-        const float4 x0 = ldg_f4(sp + (size_t)c0 * s_ns);
-        const float4 x1 = ldg_f4(sp + (size_t)c1 * s_ns);
-        float4 a0[R / 4], a1[R / 4];
-#pragma unroll
-        for (int k = 0; k < R / 4; ++k) {
-            a0[k] = ldg_f4(uval + (size_t)u * R + k * 4);
-            a1[k] = ldg_f4(uval + (size_t)(u + 1) * R + k * 4);
-        }
-#pragma unroll
-        for (int k = 0; k < R / 4; ++k) {
-            fma4(acc[4 * k + 0][0], acc[4 * k + 0][1], a0[k].x, x0);
-            fma4(acc[4 * k + 1][0], acc[4 * k + 1][1], a0[k].y, x0);
-            fma4(acc[4 * k + 2][0], acc[4 * k + 2][1], a0[k].z, x0);
-            fma4(acc[4 * k + 3][0], acc[4 * k + 3][1], a0[k].w, x0);
-        }
-#pragma unroll
-        for (int k = 0; k < R / 4; ++k) {
-            fma4(acc[4 * k + 0][0], acc[4 * k + 0][1], a1[k].x, x1);
-            fma4(acc[4 * k + 1][0], acc[4 * k + 1][1], a1[k].y, x1);
-            fma4(acc[4 * k + 2][0], acc[4 * k + 2][1], a1[k].z, x1);
-            fma4(acc[4 * k + 3][0], acc[4 * k + 3][1], a1[k].w, x1);
-        }
-    }
-    if (u < end) {
-        const int c0 = __ldg(ucol + u);
-        const float4 x0 = ldg_f4(sp + (size_t)c0 * s_ns);
-#pragma unroll
-        for (int k = 0; k < R / 4; ++k) {
-            const float4 a0 = ldg_f4(uval + (size_t)u * R + k * 4);
-            fma4(acc[4 * k + 0][0], acc[4 * k + 0][1], a0.x, x0);
-            fma4(acc[4 * k + 1][0], acc[4 * k + 1][1], a0.y, x0);
-            fma4(acc[4 * k + 2][0], acc[4 * k + 2][1], a0.z, x0);
-            fma4(acc[4 * k + 3][0], acc[4 * k + 3][1], a0.w, x0);
-        }
-    }
-    float* dp = dst + (size_t)t * d_ts + fc * 128 + lane * 4;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int row = __ldg(grp_rows + (size_t)g * R + r);
-        if (row >= 0)
-            st_f4(dp + (size_t)row * d_ns, make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y));
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // RBU v2: CTA = one group x TSPAN time steps.  The group's slab (union columns + dense [U, R]
@@ -522,13 +453,20 @@ extern "C" int sgp_spmm_rbu_halo(const int32_t* grp_ptr, const int32_t* grp_rows
     if (n_groups == 0 || Tc == 0) return SGP_OK;
     if (!src2) n_split = INT32_MAX;
     cudaStream_t st = as_stream(stream);
-    const int nfc = F / 128;
+    // tuning knobs, read once per process (never per launch)
+    static const int knob_version = getenv("SGP_B200_RBU_KERNEL") ? atoi(getenv("SGP_B200_RBU_KERNEL")) : 0;
+    static const int knob_tspan = getenv("SGP_B200_RBU_TSPAN") ? atoi(getenv("SGP_B200_RBU_TSPAN")) : 0;
+    static const int knob_minb = getenv("SGP_B200_RBU_MINB") ? atoi(getenv("SGP_B200_RBU_MINB")) : 4;
     // default: the cp.async gather ring (v3) for R = 16, register-staged gathers (v2) for R <= 8
-    const int version = getenv("SGP_B200_RBU_KERNEL") ? atoi(getenv("SGP_B200_RBU_KERNEL")) : (R == 16 ? 3 : 2);
-    const int tspan_env = getenv("SGP_B200_RBU_TSPAN") ? atoi(getenv("SGP_B200_RBU_TSPAN")) : 0;
-    if ((version == 2 || version == 3) && nfc <= 4) {
+    const int version = (knob_version == 2 || knob_version == 3) ? knob_version : (R == 16 ? 3 : 2);
+    // feature slices of at most 4 x 128 columns per launch (a CTA has one warp per 128-column chunk)
+    for (int f0 = 0; f0 < F; f0 += 512) {
+        const int nfc = (F - f0 < 512 ? F - f0 : 512) / 128;
+        const float* s1 = src + f0;
+        const float* s2 = src2 ? src2 + f0 : nullptr;
+        float* d1 = dst + f0;
         const int tpb = 4 / nfc >= 1 ? 4 / nfc : 1;          // 4 warps per CTA (nfc = 3 -> 1 step, 3 warps)
-        int tspan = tspan_env > 0 ? tspan_env : tpb;         // one time step per warp: t-major order keeps the gathered panel L2-hot
+        int tspan = knob_tspan > 0 ? knob_tspan : tpb;       // one time step per warp: t-major order keeps the gathered panel L2-hot
         tspan = ((tspan + tpb - 1) / tpb) * tpb;
         const int ny = (Tc + tspan - 1) / tspan;
         SGP_REQUIRE(ny <= 65535, SGP_EUNSUPPORTED, "sgp_spmm_rbu: Tc=%d too large for one launch", Tc);
@@ -539,41 +477,26 @@ extern "C" int sgp_spmm_rbu_halo(const int32_t* grp_ptr, const int32_t* grp_rows
     do {                                                                                         \
         SGP_CUDA(cudaFuncSetAttribute(spmm_rbu_v3<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         spmm_rbu_v3<RR><<<dim3((unsigned)n_groups, ny), nwarps * 32, smem, st>>>(                \
-            grp_ptr, grp_rows, ucol, uval, nfc, tpb, tspan, src, src_t_stride, src_n_stride, src2, \
-            src2_t_stride, src2_n_stride, n_split, dst, dst_t_stride, dst_n_stride, Tc);          \
+            grp_ptr, grp_rows, ucol, uval, nfc, tpb, tspan, s1, src_t_stride, src_n_stride, s2,  \
+            src2_t_stride, src2_n_stride, n_split, d1, dst_t_stride, dst_n_stride, Tc);           \
     } while (0)
             if (R == 4) SGP_RBU3(4);
             else if (R == 8) SGP_RBU3(8);
             else SGP_RBU3(16);
 #undef SGP_RBU3
             SGP_LAUNCH_CHECK("spmm_rbu_v3");
-            return SGP_OK;
+            continue;
         }
-        const int minb = getenv("SGP_B200_RBU_MINB") ? atoi(getenv("SGP_B200_RBU_MINB")) : 4;
 #define SGP_RBU2(RR, MB)                                                                         \
     spmm_rbu_v2<RR, MB><<<dim3((unsigned)n_groups, ny), nfc * tpb * 32, 0, st>>>(                \
-        grp_ptr, grp_rows, ucol, uval, nfc, tpb, tspan, src, src_t_stride, src_n_stride, src2,   \
-        src2_t_stride, src2_n_stride, n_split, dst, dst_t_stride, dst_n_stride, Tc)
+        grp_ptr, grp_rows, ucol, uval, nfc, tpb, tspan, s1, src_t_stride, src_n_stride, s2,      \
+        src2_t_stride, src2_n_stride, n_split, d1, dst_t_stride, dst_n_stride, Tc)
         if (R == 4) SGP_RBU2(4, 4);
         else if (R == 8) SGP_RBU2(8, 4);
-        else if (minb == 3) SGP_RBU2(16, 3);
+        else if (knob_minb == 3) SGP_RBU2(16, 3);
         else SGP_RBU2(16, 4);
 #undef SGP_RBU2
         SGP_LAUNCH_CHECK("spmm_rbu_v2");
-        return SGP_OK;
     }
-    SGP_REQUIRE(!src2, SGP_EUNSUPPORTED, "sgp_spmm_rbu: the v1 kernel has no halo source (F=%d)", F);
-    const long long total = (long long)Tc * n_groups * nfc;
-    const long long blocks = (total + kSpmmWarps - 1) / kSpmmWarps;
-    SGP_REQUIRE(blocks < (1ll << 31), SGP_EUNSUPPORTED, "sgp_spmm_rbu: too many warps for one launch");
-#define SGP_RBU(RR)                                                                              \
-    spmm_rbu_kernel<RR><<<(unsigned)blocks, kSpmmWarps * 32, 0, st>>>(                           \
-        grp_ptr, grp_rows, ucol, uval, n_groups, nfc, src, src_t_stride, src_n_stride, dst,      \
-        dst_t_stride, dst_n_stride, total)
-    if (R == 4) SGP_RBU(4);
-    else if (R == 8) SGP_RBU(8);
-    else SGP_RBU(16);
-#undef SGP_RBU
-    SGP_LAUNCH_CHECK("spmm_rbu");
     return SGP_OK;
 }

@@ -65,17 +65,53 @@ __global__ void checksum_kernel(const float* __restrict__ buf, int64_t count, do
     }
 }
 
+// acc += sum over a strided [Tc, N, F] view (the feature block a CUDA-core kernel just wrote): the
+// sink for paths whose producing kernel has no fused checksum.
+__global__ void checksum_view_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns, int N, int F,
+                                     int Tc, double* acc) {
+    double s = 0.0;
+    const int64_t rows = (int64_t)Tc * N;
+    const int lanes_f = F < 32 ? F : 32;                          // threads along the feature axis
+    const int fx = threadIdx.x % lanes_f, ry = threadIdx.x / lanes_f, rpb = blockDim.x / lanes_f;
+    if (ry < rpb)
+        for (int64_t r = (int64_t)blockIdx.x * rpb + ry; r < rows; r += (int64_t)gridDim.x * rpb) {
+            const float* p = src + (size_t)(r / N) * s_ts + (size_t)(r % N) * s_ns;
+            float part = 0.f;
+            for (int f = fx; f < F; f += lanes_f) part += __ldg(p + f);
+            s += (double)part;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double w[32];
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? w[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(acc, s);
+    }
+}
+
+// dst[t, k, :] = src[t, index[k], :] — halo packing.  VEC: 16 bytes per thread (F % 4 == 0, aligned
+// views): the rows are 0.5-1 KB, so a warp moves whole 512-byte row pieces; grid.y walks time.
+template <bool VEC>
 __global__ void gather_rows_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
                                    const int32_t* __restrict__ index, int n_index,
                                    float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int F, int Tc) {
-    const int64_t total = (int64_t)Tc * n_index * F;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int f = (int)(i % F);
-        const int64_t tn = i / F;
-        const int k = (int)(tn % n_index), t = (int)(tn / n_index);
-        dst[(size_t)t * d_ts + (size_t)k * d_ns + f] =
-            __ldg(src + (size_t)t * s_ts + (size_t)__ldg(index + k) * s_ns + f);
+    const int W = VEC ? F / 4 : F;                       // work units per row
+    const uint32_t per_t = (uint32_t)n_index * (uint32_t)W;
+    for (int t = blockIdx.y; t < Tc; t += gridDim.y) {
+        const float* sp = src + (size_t)t * s_ts;
+        float* dp = dst + (size_t)t * d_ts;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_t; i += gridDim.x * blockDim.x) {
+            const uint32_t k = i / (uint32_t)W, f = i - k * (uint32_t)W;
+            const size_t so = (size_t)__ldg(index + k) * s_ns, dofs = (size_t)k * d_ns;
+            if (VEC)
+                reinterpret_cast<float4*>(dp + dofs)[f] = ldg_f4_stream(sp + so + 4 * f);
+            else
+                dp[dofs + f] = __ldg(sp + so + f);
+        }
     }
 }
 
@@ -89,7 +125,7 @@ static int grid_1d(int64_t total, int threads) {
 
 using namespace sgp;
 
-extern "C" int sgp_version(void) { return 100; }
+extern "C" int sgp_version(void) { return SGP_B200_ABI_VERSION; }
 extern "C" const char* sgp_last_error(void) { return g_err; }
 extern "C" int64_t sgp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -132,14 +168,37 @@ extern "C" int sgp_checksum(const float* buf, int64_t count, double* acc, void* 
     return SGP_OK;
 }
 
+extern "C" int sgp_checksum_view(const float* src, int64_t src_t_stride, int64_t src_n_stride, int N, int F,
+                                 int Tc, double* acc, void* stream) {
+    SGP_REQUIRE(src && acc && N >= 0 && F >= 1 && Tc >= 0, SGP_EINVAL, "sgp_checksum_view: bad arguments");
+    const int64_t rows = (int64_t)Tc * N;
+    if (rows == 0) return SGP_OK;
+    const int lanes_f = F < 32 ? F : 32, rpb = 256 / lanes_f;
+    checksum_view_kernel<<<grid_1d(rows, rpb * 4), 256, 0, as_stream(stream)>>>(src, src_t_stride, src_n_stride,
+                                                                              N, F, Tc, acc);
+    SGP_LAUNCH_CHECK("checksum_view");
+    return SGP_OK;
+}
+
 extern "C" int sgp_gather_rows(const float* src, int64_t src_t_stride, int64_t src_n_stride,
                                const int32_t* index, int n_index, float* dst, int64_t dst_t_stride,
                                int64_t dst_n_stride, int F, int Tc, void* stream) {
     SGP_REQUIRE(src && dst && (index || n_index == 0), SGP_EINVAL, "sgp_gather_rows: null pointer");
-    const int64_t total = (int64_t)Tc * n_index * F;
-    if (total <= 0) return SGP_OK;
-    gather_rows_kernel<<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>(
-        src, src_t_stride, src_n_stride, index, n_index, dst, dst_t_stride, dst_n_stride, F, Tc);
+    if (Tc <= 0 || n_index <= 0 || F <= 0) return SGP_OK;
+    const bool vec = F % 4 == 0 && aligned16(src) && aligned16(dst) && src_t_stride % 4 == 0 &&
+                     src_n_stride % 4 == 0 && dst_t_stride % 4 == 0 && dst_n_stride % 4 == 0;
+    const int64_t per_t = (int64_t)n_index * (vec ? F / 4 : F);
+    SGP_REQUIRE(per_t < (1ll << 32), SGP_EUNSUPPORTED, "sgp_gather_rows: %d rows x %d features too large", n_index, F);
+    const int gy = Tc < 64 ? Tc : 64;
+    int gx = (int)((per_t + 255) / 256);
+    const int cap = (kNumSMs * 16 + gy - 1) / gy;
+    gx = gx < 1 ? 1 : (gx > cap ? cap : gx);
+    if (vec)
+        gather_rows_kernel<true><<<dim3(gx, gy), 256, 0, as_stream(stream)>>>(
+            src, src_t_stride, src_n_stride, index, n_index, dst, dst_t_stride, dst_n_stride, F, Tc);
+    else
+        gather_rows_kernel<false><<<dim3(gx, gy), 256, 0, as_stream(stream)>>>(
+            src, src_t_stride, src_n_stride, index, n_index, dst, dst_t_stride, dst_n_stride, F, Tc);
     SGP_LAUNCH_CHECK("gather_rows");
     return SGP_OK;
 }

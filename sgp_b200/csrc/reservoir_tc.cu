@@ -139,7 +139,7 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
                     const float* __restrict__ w_ih /* [H, Fin] */, const float* __restrict__ bias,
                     float alpha, float oma,
                     float* __restrict__ h_state, const __grid_constant__ CUtensorMap out_map,
-                    int Tc, int N, int* err, long long* trace) {
+                    int Tc, int N, int* err, double* __restrict__ chk, long long* trace) {
     constexpr int NH = H / 128;                 // output-column halves (MMA N = 128)
     constexpr int NC = H / 32;                  // k-chunks of 32
     constexpr int A_BYTES = 128 * H * 4;        // state tile
@@ -266,6 +266,7 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
         for (int f = 0; f < FINP; ++f)
             xr[f] = (live && f < Fin) ? __ldg(x + (size_t)node * x_ns + f) : 0.f;
         bool ok = true;
+        double csum = 0.0;          // fused sink: sum of every state value this thread produces (`checksum`)
         for (int t = 0; t < Tc && ok; ++t) {
             float xn[FINP];                           // x_{t+1}: in flight while this step is finished
 #pragma unroll
@@ -305,6 +306,12 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
                     hv.w = fmaf(alpha, rt_activate<ACT>(z[3]), oma * ho.w);
                     hn[j] = hv.x; hn[j + 1] = hv.y; hn[j + 2] = hv.z; hn[j + 3] = hv.w;
                 }
+                if (live) {
+                    float part = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) part += hn[j];
+                    csum += (double)part;
+                }
                 // the MMAs of this step that read the old chunk c: done for the last half when its
                 // acc_ready fired; signalled per chunk (a_free) for the halves before it
                 if (warp == 0) SGP_RT_TRACE(7 + 3 * hh, t, clock64());
@@ -317,6 +324,11 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
             }
 #pragma unroll
             for (int f = 0; f < FINP; ++f) xr[f] = xn[f];
+        }
+        if (chk != nullptr && ok) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+            if (lane == 0) atomicAdd(chk, csum);
         }
         // ---- carry the state (each warp re-reads the chunks it wrote) ----------------------------
         if (ok && live) {
@@ -476,7 +488,7 @@ extern "C" int sgp_reservoir_scan_tc(const float* x, int64_t x_t_stride, int64_t
                                      const float* wimg, const float* w_ih, const float* bias, float alpha,
                                      float one_minus_alpha, int act, float* h_state, float* out,
                                      int64_t out_t_stride, int64_t out_n_stride, int Tc, int N, int H,
-                                     int* err_flag, void* stream) {
+                                     int* err_flag, double* checksum, void* stream) {
     SGP_REQUIRE(x && wimg && w_ih && bias && h_state && out && err_flag, SGP_EINVAL,
                 "sgp_reservoir_scan_tc: null pointer");
     SGP_REQUIRE(H == 128 || H == 256, SGP_EUNSUPPORTED, "sgp_reservoir_scan_tc: H=%d (128 or 256)", H);
@@ -510,13 +522,18 @@ extern "C" int sgp_reservoir_scan_tc(const float* x, int64_t x_t_stride, int64_t
         SGP_REQUIRE(r == CUDA_SUCCESS, SGP_EINVAL, "sgp_reservoir_scan_tc: cuTensorMapEncodeTiled failed (%d): out strides %lld / %lld",
                     (int)r, (long long)out_t_stride, (long long)out_n_stride);
     }
+#ifdef SGP_RT_TRACE_ON
+    // trace builds only (tools/trace_rt.py): device buffer for the per-step timestamps of one CTA
     long long* trace_ptr = getenv("SGP_B200_RT_TRACE") ? (long long*)strtoull(getenv("SGP_B200_RT_TRACE"), nullptr, 10) : nullptr;
+#else
+    long long* trace_ptr = nullptr;
+#endif
 #define SGP_RT(H_, F_, A_)                                                                              \
     do {                                                                                                \
         SGP_CUDA(cudaFuncSetAttribute(reservoir_tc_kernel<H_, F_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         reservoir_tc_kernel<H_, F_, A_><<<grid, kRtThreads, smem, as_stream(stream)>>>(                 \
             x, x_t_stride, x_n_stride, Fin, wimg, w_ih, bias, alpha, one_minus_alpha, h_state, out_map, \
-            Tc, N, err_flag, trace_ptr);                                                                \
+            Tc, N, err_flag, checksum, trace_ptr);                                                      \
     } while (0)
 #define SGP_RT_F(H_, A_)                                                                                \
     do {                                                                                                \

@@ -165,7 +165,8 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                    int n_groups, int n_work, int group_major, int gather_policy,
                    const float* __restrict__ src, int64_t s_ts, uint32_t s_nb /* row stride, BYTES */,
                    const float* __restrict__ src2, int64_t s2_ts, uint32_t s2_nb, int n_split,
-                   float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int Tc, int* err, long long* trace) {
+                   float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int Tc, int* err, double* __restrict__ chk,
+                   long long* trace) {
     static_assert(kTcAcc == 4 && kTcABufs == 4 && kTcStages == 8, "index arithmetic below");
     constexpr int TB = kTcAcc / NFC;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -292,8 +293,9 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             for (int c = 0; c < n_chunks && ok; ++c, it += kTcAcc) {
                 const int col = coln;
                 const bool in2 = HALO && col >= n_split;
-                // byte offset of row `lane` inside its source (bit 31: the row lives in src2)
-                const uint32_t mine = in2 ? (((uint32_t)(col - n_split) * s2_nb) | 0x80000000u) : (uint32_t)col * s_nb;
+                // row `lane` of the chunk inside its source (bit 31: the row lives in src2); the byte
+                // offset is formed in 64 bits per copy (one IMAD.WIDE), so rows * stride may exceed 4 GB
+                const uint32_t mine = in2 ? ((uint32_t)(col - n_split) | 0x80000000u) : (uint32_t)col;
                 {
                     const long long nxt = (c + 1 < n_chunks) ? (long long)(c_beg + c + 1) : first_chunk_of(ws + 1);
                     if (nxt >= 0) coln = __ldg(cols + (size_t)nxt * kTcKC + lane);
@@ -305,8 +307,8 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                 const uint32_t dst = dst0 + s * kTcStageBytes, fbar = full0 + s * 8;
 #pragma unroll
                 for (int j = 0; j < kTcKC; ++j) {
-                    const uint32_t off = __shfl_sync(0xffffffffu, mine, j);
-                    const char* p = (HALO && (off >> 31)) ? b2 + (off & 0x7fffffffu) : b1 + off;
+                    const uint32_t r = __shfl_sync(0xffffffffu, mine, j);
+                    const char* p = (HALO && (r >> 31)) ? b2 + (uint64_t)(r & 0x7fffffffu) * s2_nb : b1 + (uint64_t)r * s_nb;
                     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n"
                                  :: "r"(dst + j * 512), "l"(p), "l"(pol_keep));
                 }
@@ -333,6 +335,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         const uint32_t d_nb = (uint32_t)d_ns * 4u;                 // row stride in bytes (host checks < 2^32)
         int it0 = 0, cc = 0, wn = 0;
         bool ok = true;
+        double csum = 0.0;          // fused sink: sum of every value this thread stores
         // rows [16, 64) of the previous work item's accumulator, waiting to be stored
         uint32_t pa[16], pb[16], pc[16];     // three separate arrays: they must stay in registers
         int pending = 0, p_row0 = -1, p_row1 = -1;
@@ -342,10 +345,14 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
 #pragma unroll
             for (int e2 = 0; e2 < 16; ++e2)
                 rows[e2] = __shfl_sync(0xffffffffu, (j0 < 32) ? r0 : r1, (j0 & 31) + e2);
+            float part = 0.f;
 #pragma unroll
             for (int e2 = 0; e2 < 16; ++e2)
-                if (dp != nullptr && rows[e2] >= 0)
+                if (dp != nullptr && rows[e2] >= 0) {
                     asm volatile("st.global.cs.b32 [%0], %1;" :: "l"(dp + (uint64_t)(uint32_t)rows[e2] * d_nb), "r"(v[e2]) : "memory");
+                    part += __uint_as_float(v[e2]);
+                }
+            csum += (double)part;
         };
         // store 16 of the pending rows (register indices must be compile-time constants)
         auto service = [&]() {
@@ -445,6 +452,11 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             pending = 48; p_row0 = my_row0; p_row1 = my_row1; p_dp = dp;
         }
         while (ok && pending > 0) service();
+        if (chk != nullptr && ok) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+            if (lane == 0) atomicAdd(chk, csum);
+        }
 #else
     } else if (warp < kTcSplitWarps) {
         // ================= split warps: stage (smem) -> A hi | lo tiles (TMEM); epilogue =======
@@ -453,6 +465,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
         int it0 = 0, cc = 0, wn = 0;                               // items, chunks, non-empty work items so far
         bool ok = true;
+        double csum = 0.0;          // fused sink: sum of every value this thread stores (sgp_spmm_rbu_tc `checksum`)
         // one chunk's item of my accumulator: ring stage -> A tile (hi | lo) in TMEM
         auto convert_item = [&]() -> bool {
             const int a = grp;
@@ -550,14 +563,23 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
 #pragma unroll
                     for (int e2 = 0; e2 < 16; ++e2) v[e2] = 0u;          // group without entries: zero rows
                 }
+                float part = 0.f;
 #pragma unroll
                 for (int e2 = 0; e2 < 16; ++e2) {
-                    if (t_ok && rows[e2] >= 0)
+                    if (t_ok && rows[e2] >= 0) {
                         asm volatile("st.global.cs.b32 [%0], %1;"      // streaming (evict-first): written once, read by the next hop's launch
                                      :: "l"(dp + (uint64_t)(uint32_t)rows[e2] * d_nb), "r"(v[e2]) : "memory");
+                        part += __uint_as_float(v[e2]);
+                    }
                 }
+                csum += (double)part;
             }
             if (n_chunks > 0) ++wn;
+        }
+        if (chk != nullptr && ok) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+            if (lane == 0) atomicAdd(chk, csum);
         }
 #endif
     } else if (warp == kTcSplitWarps + kTcProducerWarps + kTcIssuers) {
@@ -700,11 +722,30 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
 
 using namespace sgp;
 
+namespace {
+// Tuning knobs are read from the environment ONCE, at the first launch of the process (not per
+// call: the ABI is re-entrant across streams and must not depend on hidden mutable state).
+struct TcKnobs {
+    int group_major, gather_policy;
+    TcKnobs() {
+        const char* o = getenv("SGP_B200_TC_ORDER");
+        group_major = o && o[0] == 'g';
+        const char* g = getenv("SGP_B200_TC_GATHER");
+        gather_policy = g ? atoi(g) : 0;            // 0 evict_last, 1 normal, 2 evict_first
+    }
+};
+const TcKnobs& tc_knobs() {
+    static const TcKnobs k;
+    return k;
+}
+}  // namespace
+
 extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int32_t* cols,
                                const float* bimg, int n_groups, const float* src, int64_t src_t_stride,
                                int64_t src_n_stride, const float* src2, int64_t src2_t_stride,
                                int64_t src2_n_stride, int n_split, float* dst, int64_t dst_t_stride,
-                               int64_t dst_n_stride, int F, int Tc, int* err_flag, void* stream) {
+                               int64_t dst_n_stride, int F, int Tc, int* err_flag, double* checksum,
+                               void* stream) {
     SGP_REQUIRE(chunk_ptr && grp_rows && cols && bimg && src && dst && err_flag, SGP_EINVAL,
                 "sgp_spmm_rbu_tc: null pointer");
     const int nfc = F / 128;
@@ -719,24 +760,28 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
     const int tb = kTcAcc / nfc;
     const int ny = (Tc + tb - 1) / tb;
     SGP_REQUIRE(ny <= 65535, SGP_EUNSUPPORTED, "sgp_spmm_rbu_tc: Tc=%d too large for one launch", Tc);
-    // gathered-row byte offsets are 32-bit inside the kernel
-    SGP_REQUIRE(src_n_stride > 0 && src_n_stride * 4 < (1ll << 31) / 64 && (!src2 || (src2_n_stride > 0 && src2_n_stride * 4 < (1ll << 31) / 64)),
+    // row strides travel as 32-bit byte counts; row * stride is formed in 64 bits inside the kernel
+    SGP_REQUIRE(src_n_stride > 0 && src_n_stride * 4 < (1ll << 32) && (!src2 || (src2_n_stride > 0 && src2_n_stride * 4 < (1ll << 32))),
                 SGP_EUNSUPPORTED, "sgp_spmm_rbu_tc: row stride too large");
     SGP_REQUIRE(dst_n_stride > 0 && dst_n_stride * 4 < (1ll << 32), SGP_EUNSUPPORTED, "sgp_spmm_rbu_tc: dst row stride too large");
     const uint32_t s_nb = (uint32_t)(src_n_stride * 4), s2_nb = (uint32_t)(src2_n_stride * 4);
     const int n_work = n_groups * ny;
-    const int group_major = getenv("SGP_B200_TC_ORDER") && getenv("SGP_B200_TC_ORDER")[0] == 'g';
-    const int gather_policy = getenv("SGP_B200_TC_GATHER") ? atoi(getenv("SGP_B200_TC_GATHER")) : 0;   // 0 evict_last, 1 normal, 2 evict_first
+    const int group_major = tc_knobs().group_major, gather_policy = tc_knobs().gather_policy;
     const int n_par = group_major ? n_groups : n_work;
     const int grid = n_par < kNumSMs ? n_par : kNumSMs;          // persistent: one CTA per SM
+#ifdef SGP_TC_TRACE
+    // trace builds only (tools/trace_tc.py): device buffer for the per-item timestamps of one CTA
     long long* trace_ptr = getenv("SGP_B200_TC_TRACE") ? (long long*)strtoull(getenv("SGP_B200_TC_TRACE"), nullptr, 10) : nullptr;
+#else
+    long long* trace_ptr = nullptr;
+#endif
 #define SGP_TC3(NFC_, HALO_, PW_)                                                                      \
     do {                                                                                               \
         SGP_CUDA(cudaFuncSetAttribute(spmm_rbu_tc_kernel<NFC_, HALO_, PW_>,                            \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));     \
         spmm_rbu_tc_kernel<NFC_, HALO_, PW_><<<grid, (kTcSplitWarps + PW_ + kTcIssuers + kTcPadWarps) * 32, kTcSmem, as_stream(stream)>>>( \
             chunk_ptr, grp_rows, cols, bimg, n_groups, n_work, group_major, gather_policy, src, src_t_stride, s_nb, src2, \
-            src2_t_stride, s2_nb, n_split, dst, dst_t_stride, dst_n_stride, Tc, err_flag, trace_ptr);  \
+            src2_t_stride, s2_nb, n_split, dst, dst_t_stride, dst_n_stride, Tc, err_flag, checksum, trace_ptr);  \
     } while (0)
 #define SGP_TC(NFC_, HALO_)                                                                            \
     do {                                                                                               \

@@ -95,10 +95,11 @@ class SGPSpatialEncoder(nn.Module):
                               rbu=self.rbu_mode)
 
     def encode_chunk(self, buf: Tensor, F: int, fwd: ShiftOperator, bwd: Optional[ShiftOperator],
-                     sums: Optional[Tensor] = None) -> None:
-        """buf [Tc, N, num_blocks*F] (device) with block 0 filled; fills the other blocks."""
+                     sums: Optional[Tensor] = None, checksum: Optional[Tensor] = None) -> None:
+        """buf [Tc, N, num_blocks*F] (device) with block 0 filled; fills the other blocks.
+        `checksum` (device float64 scalar) += the sum of every block written here."""
         k = self.receptive_field
-        propagate_into(buf, F, k, fwd, bwd)
+        propagate_into(buf, F, k, fwd, bwd, checksum)
         if self.global_attr:
             Tc, N, _ = buf.shape
             if sums is None:
@@ -106,6 +107,8 @@ class SGPSpatialEncoder(nn.Module):
             ops.node_sum(buf[..., :F], sums[:Tc])
             g = spatial_blocks(k, self.bidirectional)
             ops.node_mean_broadcast(sums[:Tc], N, buf[..., g * F:(g + 1) * F])
+            if checksum is not None:
+                ops.checksum_view(buf[..., g * F:(g + 1) * F], checksum)
 
     def forward(self, x, edge_index, edge_weight):
         """x [T, N, F] (or [N, F]) on CPU or GPU -> [T, N, num_blocks*F] on the same device."""
@@ -158,10 +161,12 @@ class SGPEncoder(nn.Module):
         return self.sgp_encoder.num_blocks() * self.reservoir.num_layers * self.reservoir.hidden_size
 
     def encode_stream(self, x: Tensor, edge_index, edge_weight,
-                      sink: Callable[[int, int, Tensor], None], device=None,
-                      operators=None) -> None:
+                      sink: Optional[Callable[[int, int, Tensor], None]], device=None,
+                      operators=None, checksum: Optional[Tensor] = None) -> None:
         """Encode x [T, N, Fin] chunk by chunk; ``sink(t0, t1, chunk)`` receives each finished
-        [t1-t0, N, D] device buffer (valid until the next-but-one call: two buffers alternate)."""
+        [t1-t0, N, D] device buffer (valid until the next-but-one call: two buffers alternate).
+        ``checksum`` (device float64 scalar) += the sum of the whole [T, N, D] output, accumulated
+        by the producing kernels themselves; with it ``sink`` may be None (a pure streaming run)."""
         T, N, Fin = x.shape
         dev = torch.device(device) if device is not None else _cuda_device_for(x)
         res, spat = self.reservoir, self.sgp_encoder
@@ -178,9 +183,10 @@ class SGPEncoder(nn.Module):
             t1 = min(T, t0 + step)
             buf = bufs[i % len(bufs)][: t1 - t0]
             xc = x[t0:t1].detach().to(device=dev, dtype=torch.float32, non_blocking=True)
-            res.scan_chunk(plan, xc, state, buf)
-            spat.encode_chunk(buf, F, fwd, bwd, sums)
-            sink(t0, t1, buf)
+            res.scan_chunk(plan, xc, state, buf, checksum)
+            spat.encode_chunk(buf, F, fwd, bwd, sums, checksum)
+            if sink is not None:
+                sink(t0, t1, buf)
         for op in (fwd, bwd):
             if op is not None:
                 op.check()

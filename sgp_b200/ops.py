@@ -25,6 +25,14 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _call(dev, name: str, *args) -> None:
+    """One C-ABI launch with `dev` as the CURRENT CUDA device (kernel launches, cudaFuncSetAttribute
+    and the cub calls inside the library all act on the current device, which need not be the
+    tensors' device when the caller works on several GPUs)."""
+    with torch.cuda.device(dev):
+        check(getattr(load(), name)(*args), name)
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -71,8 +79,8 @@ def csr_build(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     nnz = ctypes.c_int64(0)
     src, dst = (ei[0], ei[1]) if E else (None, None)
-    check(lib.sgp_csr_build(_p(src), _p(dst), _p(w), E, N, flags, _p(rowptr), _p(col), _p(val), cap,
-                            ctypes.byref(nnz), _p(ws), ws_bytes, _stream(dev)), "sgp_csr_build")
+    _call(dev, "sgp_csr_build", _p(src), _p(dst), _p(w), E, N, flags, _p(rowptr), _p(col), _p(val), cap,
+                            ctypes.byref(nnz), _p(ws), ws_bytes, _stream(dev))
     n = int(nnz.value)
     return Csr(rowptr, col[:n], val[:n], N)
 
@@ -82,8 +90,8 @@ def reservoir_pack(w_ih: torch.Tensor, w_hh: torch.Tensor) -> torch.Tensor:
     H, Fin = w_ih.shape
     rows = int(load().sgp_reservoir_pack_rows(Fin, H))
     out = torch.empty(rows, H, dtype=torch.float32, device=w_ih.device)
-    check(load().sgp_reservoir_pack(_p(w_ih.contiguous()), _p(w_hh.contiguous()), Fin, H, _p(out),
-                                    _stream(w_ih.device)), "sgp_reservoir_pack")
+    _call(w_ih.device, "sgp_reservoir_pack", _p(w_ih.contiguous()), _p(w_hh.contiguous()), Fin, H, _p(out),
+                                    _stream(w_ih.device))
     return out
 
 
@@ -97,10 +105,10 @@ def reservoir_scan(x: torch.Tensor, wpack: torch.Tensor, bias: torch.Tensor, alp
     H = int(bias.numel())
     assert out.shape == (Tc, N, H) and h_state.shape == (N, H) and h_state.is_contiguous()
     a = float(alpha)
-    check(load().sgp_reservoir_scan(_p(x), x.stride(0), x.stride(1), Fin, _p(wpack), _p(bias),
+    _call(x.device, "sgp_reservoir_scan", _p(x), x.stride(0), x.stride(1), Fin, _p(wpack), _p(bias),
                                     a, float(1.0 - a), ACT_CODES[activation], _p(h_state),
                                     _p(out), out.stride(0), out.stride(1), Tc, N, H,
-                                    _stream(x.device)), "sgp_reservoir_scan")
+                                    _stream(x.device))
 
 
 def reservoir_tc_pack(w_hh: torch.Tensor) -> torch.Tensor:
@@ -108,15 +116,15 @@ def reservoir_tc_pack(w_hh: torch.Tensor) -> torch.Tensor:
     _require_cuda(w_hh)
     H = int(w_hh.shape[0])
     out = torch.empty(2 * H * H, dtype=torch.float32, device=w_hh.device)
-    check(load().sgp_reservoir_tc_pack(_p(w_hh.contiguous()), H, _p(out), _stream(w_hh.device)),
-          "sgp_reservoir_tc_pack")
+    _call(w_hh.device, "sgp_reservoir_tc_pack", _p(w_hh.contiguous()), H, _p(out), _stream(w_hh.device))
     return out
 
 
 def reservoir_scan_tc(x: torch.Tensor, wimg: torch.Tensor, w_ih: torch.Tensor, bias: torch.Tensor,
                       alpha: float, activation: str, h_state: torch.Tensor, out: torch.Tensor,
-                      err: torch.Tensor) -> None:
-    """Tensor-core variant of reservoir_scan (same views); `err` is a device int32 flag."""
+                      err: torch.Tensor, checksum: Optional[torch.Tensor] = None) -> None:
+    """Tensor-core variant of reservoir_scan (same views); `err` is a device int32 flag, `checksum`
+    an optional device float64 scalar that receives the sum of everything written to `out`."""
     _require_cuda(x, wimg, w_ih, bias, h_state, out, err)
     _check_view3(x, "x")
     _check_view3(out, "out")
@@ -124,10 +132,9 @@ def reservoir_scan_tc(x: torch.Tensor, wimg: torch.Tensor, w_ih: torch.Tensor, b
     H = int(bias.numel())
     assert out.shape == (Tc, N, H) and h_state.shape == (N, H) and h_state.is_contiguous()
     a = float(alpha)
-    check(load().sgp_reservoir_scan_tc(_p(x), x.stride(0), x.stride(1), Fin, _p(wimg), _p(w_ih), _p(bias),
+    _call(x.device, "sgp_reservoir_scan_tc", _p(x), x.stride(0), x.stride(1), Fin, _p(wimg), _p(w_ih), _p(bias),
                                        a, float(1.0 - a), ACT_CODES[activation], _p(h_state), _p(out),
-                                       out.stride(0), out.stride(1), Tc, N, H, _p(err), _stream(x.device)),
-          "sgp_reservoir_scan_tc")
+                                       out.stride(0), out.stride(1), Tc, N, H, _p(err), _p(checksum), _stream(x.device))
 
 
 def spmm(csr: Csr, src: torch.Tensor, dst: torch.Tensor, row_order: Optional[torch.Tensor] = None,
@@ -143,10 +150,10 @@ def spmm(csr: Csr, src: torch.Tensor, dst: torch.Tensor, row_order: Optional[tor
     else:
         _check_view3(halo, "halo")
         h_ptr, h_ts, h_ns = _p(halo), halo.stride(0), halo.stride(1)
-    check(load().sgp_spmm_halo(_p(csr.rowptr), _p(csr.col), _p(csr.val), _p(row_order),
+    _call(src.device, "sgp_spmm_halo", _p(csr.rowptr), _p(csr.col), _p(csr.val), _p(row_order),
                                _p(src), src.stride(0), src.stride(1), h_ptr, h_ts, h_ns, n_split,
                                _p(dst), dst.stride(0), dst.stride(1), rows, F, Tc,
-                               _stream(src.device)), "sgp_spmm")
+                               _stream(src.device))
 
 
 def khop_spmm(csr: Csr, buf: torch.Tensor, block_in: int, block_out0: int, hops: int, F: int,
@@ -154,9 +161,9 @@ def khop_spmm(csr: Csr, buf: torch.Tensor, block_in: int, block_out0: int, hops:
     _require_cuda(buf)
     _check_view3(buf, "buf")
     Tc, N, _ = buf.shape
-    check(load().sgp_khop_spmm(_p(csr.rowptr), _p(csr.col), _p(csr.val), _p(row_order), _p(buf),
+    _call(buf.device, "sgp_khop_spmm", _p(csr.rowptr), _p(csr.col), _p(csr.val), _p(row_order), _p(buf),
                                buf.stride(0), buf.stride(1), block_in, block_out0, hops, N, F, Tc,
-                               _stream(buf.device)), "sgp_khop_spmm")
+                               _stream(buf.device))
 
 
 @dataclass
@@ -180,9 +187,19 @@ def group_rows_host(rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, N: int
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     col = np.ascontiguousarray(col, np.int32)
     val = np.ascontiguousarray(val, np.float32)
-    check(lib.sgp_group_rows(rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, N, R,
+    check(load().sgp_group_rows(rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, N, R,
                              out.ctypes.data, ctypes.byref(got)), "sgp_group_rows")
     return out[: n_groups * R].reshape(n_groups, R)
+
+
+def partition_rows_host(rowptr: np.ndarray, col: np.ndarray, N: int, parts: int) -> np.ndarray:
+    """Host recursive bisection (csrc/group_rows.cu::sgp_partition_rows): owner [N] int32."""
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    col = np.ascontiguousarray(col, np.int32)
+    owner = np.empty(max(N, 1), np.int32)
+    check(load().sgp_partition_rows(rowptr.ctypes.data, col.ctypes.data, N, parts, owner.ctypes.data),
+          "sgp_partition_rows")
+    return owner[:N]
 
 
 def rbu_build(csr: Csr, R: int, grp_rows_h: Optional[np.ndarray] = None,
@@ -231,10 +248,10 @@ def spmm_rbu(rbu: Rbu, src: torch.Tensor, dst: torch.Tensor, halo: Optional[torc
     else:
         _check_view3(halo, "halo")
         h_ptr, h_ts, h_ns = _p(halo), halo.stride(0), halo.stride(1)
-    check(load().sgp_spmm_rbu_halo(_p(rbu.grp_ptr), _p(rbu.grp_rows), _p(rbu.ucol), _p(rbu.uval), rbu.R,
+    _call(src.device, "sgp_spmm_rbu_halo", _p(rbu.grp_ptr), _p(rbu.grp_rows), _p(rbu.ucol), _p(rbu.uval), rbu.R,
                                    rbu.n_groups, _p(src), src.stride(0), src.stride(1), h_ptr, h_ts, h_ns,
                                    n_split, _p(dst), dst.stride(0), dst.stride(1), F, Tc,
-                                   _stream(src.device)), "sgp_spmm_rbu")
+                                   _stream(src.device))
 
 
 @dataclass
@@ -304,7 +321,7 @@ def tc_build(csr: Csr, grp_rows_h: Optional[np.ndarray] = None, n_cols: Optional
 
 
 def spmm_tc(tc: TcOp, src: torch.Tensor, dst: torch.Tensor, halo: Optional[torch.Tensor] = None,
-            n_split: int = 0) -> None:
+            n_split: int = 0, checksum: Optional[torch.Tensor] = None) -> None:
     _require_cuda(src, dst, halo)
     _check_view3(src, "src")
     _check_view3(dst, "dst")
@@ -314,10 +331,10 @@ def spmm_tc(tc: TcOp, src: torch.Tensor, dst: torch.Tensor, halo: Optional[torch
     else:
         _check_view3(halo, "halo")
         h_ptr, h_ts, h_ns = _p(halo), halo.stride(0), halo.stride(1)
-    check(load().sgp_spmm_rbu_tc(_p(tc.chunk_ptr), _p(tc.grp_rows), _p(tc.cols), _p(tc.bimg), tc.n_groups,
+    _call(src.device, "sgp_spmm_rbu_tc", _p(tc.chunk_ptr), _p(tc.grp_rows), _p(tc.cols), _p(tc.bimg), tc.n_groups,
                                  _p(src), src.stride(0), src.stride(1), h_ptr, h_ts, h_ns, n_split,
-                                 _p(dst), dst.stride(0), dst.stride(1), F, Tc, _p(tc.err),
-                                 _stream(src.device)), "sgp_spmm_rbu_tc")
+                                 _p(dst), dst.stride(0), dst.stride(1), F, Tc, _p(tc.err), _p(checksum),
+                                 _stream(src.device))
 
 
 def tc_check(tc: TcOp) -> None:
@@ -330,26 +347,34 @@ def node_sum(src: torch.Tensor, sums: torch.Tensor) -> None:
     _check_view3(src, "src")
     Tc, N, F = src.shape
     assert sums.shape == (Tc, F) and sums.is_contiguous()
-    check(load().sgp_node_sum(_p(src), src.stride(0), src.stride(1), _p(sums), N, F, Tc,
-                              _stream(src.device)), "sgp_node_sum")
+    _call(src.device, "sgp_node_sum", _p(src), src.stride(0), src.stride(1), _p(sums), N, F, Tc,
+                              _stream(src.device))
 
 
 def node_mean_broadcast(sums: torch.Tensor, n_total: int, dst: torch.Tensor) -> None:
     _check_view3(dst, "dst")
     Tc, N, F = dst.shape
-    check(load().sgp_node_mean_broadcast(_p(sums), n_total, _p(dst), dst.stride(0), dst.stride(1),
-                                         N, F, Tc, _stream(dst.device)), "sgp_node_mean_broadcast")
+    _call(dst.device, "sgp_node_mean_broadcast", _p(sums), n_total, _p(dst), dst.stride(0), dst.stride(1),
+                                         N, F, Tc, _stream(dst.device))
 
 
 def checksum(buf: torch.Tensor, acc: torch.Tensor) -> None:
     assert buf.is_contiguous() and buf.dtype == torch.float32 and acc.dtype == torch.float64
-    check(load().sgp_checksum(_p(buf), buf.numel(), _p(acc), _stream(buf.device)), "sgp_checksum")
+    _call(buf.device, "sgp_checksum", _p(buf), buf.numel(), _p(acc), _stream(buf.device))
+
+
+def checksum_view(view: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc += sum(view) for a [T, N, F] float32 view with contiguous features (fp64 accumulation)."""
+    _check_view3(view, "view")
+    assert acc.dtype == torch.float64
+    Tc, N, F = view.shape
+    _call(view.device, "sgp_checksum_view", _p(view), view.stride(0), view.stride(1), N, F, Tc, _p(acc),
+          _stream(view.device))
 
 
 def gather_rows(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> None:
     _check_view3(src, "src")
     _check_view3(dst, "dst")
     Tc, _, F = src.shape
-    check(load().sgp_gather_rows(_p(src), src.stride(0), src.stride(1), _p(index), int(index.numel()),
-                                 _p(dst), dst.stride(0), dst.stride(1), F, Tc, _stream(src.device)),
-          "sgp_gather_rows")
+    _call(src.device, "sgp_gather_rows", _p(src), src.stride(0), src.stride(1), _p(index), int(index.numel()),
+                                 _p(dst), dst.stride(0), dst.stride(1), F, Tc, _stream(src.device))

@@ -77,18 +77,24 @@ class ShiftOperator:
                 self.rbu = cand
                 return
 
-    def apply(self, src: Tensor, dst: Tensor, halo: Optional[Tensor] = None) -> None:
+    def apply(self, src: Tensor, dst: Tensor, halo: Optional[Tensor] = None,
+              checksum: Optional[Tensor] = None) -> None:
         """dst[t] = S @ src[t] for [T, N, F] device views (dst must not alias src); with `halo`
-        [T, n_halo, F] the operator's column ids >= n_split read halo rows."""
+        [T, n_halo, F] the operator's column ids >= n_split read halo rows.  `checksum` (device
+        float64 scalar) += sum(dst): fused into the tensor-core hop's epilogue, a separate
+        reduction over dst for the CUDA-core kernels."""
         F = src.size(-1)
         aligned = (F % 128 == 0 and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0 and
                    all(s % 4 == 0 for s in (*src.stride()[:2], *dst.stride()[:2])))
         if self.tc is not None and aligned and (F // 128) in (1, 2, 4):
-            ops.spmm_tc(self.tc, src, dst, halo, self.n_split)
-        elif self.rbu is not None and aligned:
+            ops.spmm_tc(self.tc, src, dst, halo, self.n_split, checksum)
+            return
+        if self.rbu is not None and aligned:
             ops.spmm_rbu(self.rbu, src, dst, halo, self.n_split)
         else:
             ops.spmm(self.csr, src, dst, halo=halo, n_split=self.n_split)
+        if checksum is not None:
+            ops.checksum_view(dst[:, :self.num_nodes], checksum)
 
     def check(self) -> None:
         """Raise if a tensor-core launch of this operator reported a barrier timeout (syncs)."""
@@ -170,16 +176,16 @@ def spatial_blocks(k: int, bidirectional: bool) -> int:
 
 
 def propagate_into(buf: Tensor, F: int, k: int, fwd: ShiftOperator,
-                   bwd: Optional[ShiftOperator]) -> None:
+                   bwd: Optional[ShiftOperator], checksum: Optional[Tensor] = None) -> None:
     """buf [T, N, >= blocks*F] on the device with block 0 filled: write S^h x into block h for
     h = 1..k and, with `bwd`, the k hops of the reversed operator into blocks k+1..2k
     (the order of the reference's ``res`` list, sgp_preprocessing.py:200-217)."""
     for h in range(1, k + 1):
-        fwd.apply(buf[..., (h - 1) * F:h * F], buf[..., h * F:(h + 1) * F])
+        fwd.apply(buf[..., (h - 1) * F:h * F], buf[..., h * F:(h + 1) * F], checksum=checksum)
     if bwd is not None:
         for h in range(1, k + 1):
             src = buf[..., :F] if h == 1 else buf[..., (k + h - 1) * F:(k + h) * F]
-            bwd.apply(src, buf[..., (k + h) * F:(k + h + 1) * F])
+            bwd.apply(src, buf[..., (k + h) * F:(k + h + 1) * F], checksum=checksum)
 
 
 def make_operators(edge_index, edge_weight, num_nodes, *, undirected, add_self_loops,

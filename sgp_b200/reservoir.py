@@ -161,19 +161,24 @@ class Reservoir(nn.Module):
                 plan.append(("cuda", *layer.device_weights(device), float(layer.alpha)))
         return plan
 
-    def scan_chunk(self, plan, x_chunk: torch.Tensor, h_state: torch.Tensor, out: torch.Tensor) -> None:
+    def scan_chunk(self, plan, x_chunk: torch.Tensor, h_state: torch.Tensor, out: torch.Tensor,
+                   checksum: Optional[torch.Tensor] = None) -> None:
         """Advance all layers over one chunk.  x_chunk [Tc,N,Fin] (device), h_state [L,N,H] in/out,
-        out [Tc,N,>=L*H] view: layer l writes features [l*H,(l+1)*H) and reads layer l-1's block."""
+        out [Tc,N,>=L*H] view: layer l writes features [l*H,(l+1)*H) and reads layer l-1's block.
+        `checksum` (device float64 scalar): += the sum of every state written (the streaming sink:
+        fused into the tensor-core scan's epilogue, a separate reduction for the CUDA-core scan)."""
         H = self.hidden_size
         inp = x_chunk
         for l, entry in enumerate(plan):
             blk = out[..., l * H:(l + 1) * H]
             if entry[0] == "tc":
                 _, wimg, w_ih, b, alpha, err = entry
-                ops.reservoir_scan_tc(inp, wimg, w_ih, b, alpha, self.mode, h_state[l], blk, err)
+                ops.reservoir_scan_tc(inp, wimg, w_ih, b, alpha, self.mode, h_state[l], blk, err, checksum)
             else:
                 _, wpack, b, alpha = entry
                 ops.reservoir_scan(inp, wpack, b, alpha, self.mode, h_state[l], blk)
+                if checksum is not None:
+                    ops.checksum_view(blk, checksum)
             inp = blk
 
     @staticmethod

@@ -4,30 +4,36 @@ The reference is single-process; this is the B200-side scaling design named by t
 
 * the reservoir is embarrassingly parallel over nodes (shared frozen weights, per-node state) —
   every rank scans only its own rows, no communication;
-* the K-hop propagation is sharded by DESTINATION rows: rank r owns a contiguous range of the
-  locality-ordered row groups (the same breadth-first greedy groups the RBU kernel uses), i.e. a
-  compact patch of the sensor graph, plus the matching rows of every feature block;
+* the K-hop propagation is sharded by DESTINATION rows: rank r owns one compact patch of the
+  sensor graph (recursive bisection along the patch diameter, csrc/group_rows.cu::
+  sgp_partition_rows — halo rows per owned row 0.05 / 0.10 / 0.19 at 2 / 4 / 8 ranks on the
+  100k-node 100-NN graph) plus the matching rows of every feature block;
 * before each hop the rows of the previous block that other ranks reference ("halo" rows) are
-  packed on the device (sgp_gather_rows) and exchanged with ONE all-to-all-v over NVLink; the
-  SpMM kernels then read local columns from the rank's own block and halo columns straight
-  from the receive buffer (second source pointer, no concatenation copy);
-* two chunks are in flight on two CUDA streams so that the exchange of one overlaps the SpMM of
-  the other.
+  packed on the device (sgp_gather_rows, 16 bytes per thread) and exchanged with ONE all-to-all-v
+  over NVLink; the SpMM kernels then read local columns from the rank's own block and halo
+  columns straight from the receive buffer (second source pointer, no concatenation copy);
+* bidirectional / undirected encoders shard the reversed / symmetrised operator by the SAME row
+  partition, each with its own halo plan;
+* chunks of time steps flow through a 3-stage pipeline on three CUDA streams: the scan of chunk
+  c + 1 (serial in time: carried state) runs on its own stream while the hop chains of chunks c
+  and c - 1 alternate on two others, so that the exchange of one overlaps the SpMM of the other;
+  hand-offs are per-chunk events (scan done -> hops may start, sink done -> buffer reusable).
 
-The partition / halo plan is plain numpy, identical on every rank (deterministic from the CSR),
-and is what the world_size-2 gloo tests check on CPU.
+The partition / halo plan is numpy + one host C++ call, identical on every rank (deterministic
+from the CSR), and is what the world_size-2 gloo tests check on CPU.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, List, Optional
+from typing import Callable, Dict, List, Optional
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import ops
-from .preprocessing import ShiftOperator
+from ._lib import SgpError
+from .preprocessing import ShiftOperator, build_operator, spatial_blocks
 
 
 # --------------------------------------------------------------------------------------------
@@ -46,7 +52,6 @@ class ShardPlan:
     rowptr: np.ndarray         # local CSR over own rows; columns renumbered [own | halo]
     col: np.ndarray
     val: np.ndarray
-    grp_rows: np.ndarray       # [n_groups_local, R] local row ids per RBU group (-1 padding)
 
     @property
     def n_own(self) -> int:
@@ -57,44 +62,34 @@ class ShardPlan:
         return int(self.halo.size)
 
 
-def partition_rows(rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, num_nodes: int,
-                   world: int, R: int = 16):
-    """owner[node] and the per-rank ordered row lists: contiguous ranges of the locality-ordered
-    R-row groups, balanced by group count."""
-    groups = ops.group_rows_host(rowptr, col, val, num_nodes, R)          # [n_groups, R]
-    n_groups = groups.shape[0]
-    bounds = [(n_groups * r) // world for r in range(world + 1)]
-    owner = np.empty(num_nodes, np.int32)
-    owned, grp_local = [], []
-    for r in range(world):
-        g = groups[bounds[r]:bounds[r + 1]]
-        flat = g.reshape(-1)
-        ids = flat[flat >= 0].astype(np.int64)
-        owner[ids] = r
-        owned.append(ids)
-        loc = np.full(flat.shape, -1, np.int32)
-        loc[flat >= 0] = np.arange(ids.size, dtype=np.int32)
-        grp_local.append(loc.reshape(-1, R))
-    return owner, owned, grp_local
+def partition_rows(rowptr: np.ndarray, col: np.ndarray, num_nodes: int, world: int) -> np.ndarray:
+    """owner[node] in [0, world): compact, equally sized graph patches (host C++)."""
+    if world == 1:
+        return np.zeros(num_nodes, np.int32)
+    return ops.partition_rows_host(rowptr, col, num_nodes, world)
 
 
 def build_plans(rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, num_nodes: int, world: int,
-                R: int = 16, ranks: Optional[List[int]] = None) -> List[ShardPlan]:
-    """Plans for `ranks` (default: all).  Every rank can call this with ranks=[its own rank]."""
+                ranks: Optional[List[int]] = None, owner: Optional[np.ndarray] = None) -> List[ShardPlan]:
+    """Plans for `ranks` (default: all).  Every rank can call this with ranks=[its own rank].
+    `owner` [N] fixes the row partition (a second operator over the same nodes — the reversed
+    graph of a bidirectional encoder — must use the partition of the first)."""
     N = int(num_nodes)
     rowptr = np.asarray(rowptr, np.int64)
     col = np.asarray(col, np.int64)
-    owner, owned, grp_local = partition_rows(rowptr, col, val, N, world, R)
+    if owner is None:
+        owner = partition_rows(rowptr, col, N, world)
+    owner = np.asarray(owner, np.int64)
     deg = np.diff(rowptr)
     row_of_e = np.repeat(np.arange(N, dtype=np.int64), deg)
-    ro, co = owner[row_of_e].astype(np.int64), owner[col].astype(np.int64)
+    ro, co = owner[row_of_e], owner[col]
     cross = ro != co
     # distinct (receiving rank p, source rank q, node j), sorted by (p, q, j)
     key = np.unique((ro[cross] * world + co[cross]) * N + col[cross])
     p_of, q_of, j_of = key // (world * N), (key // N) % world, key % N
     plans = []
     for r in (ranks if ranks is not None else range(world)):
-        own = owned[r]
+        own = np.flatnonzero(owner == r).astype(np.int64)         # ascending global id
         mine = p_of == r
         halo = j_of[mine]
         recv_counts = np.bincount(q_of[mine], minlength=world).astype(np.int64)
@@ -113,115 +108,290 @@ def build_plans(rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, num_nodes:
         assert (lcol >= 0).all()
         plans.append(ShardPlan(r, world, N, own, halo, recv_counts, send_index.astype(np.int32),
                                send_counts, lrowptr.astype(np.int32), lcol.astype(np.int32),
-                               np.asarray(val, np.float32)[idx], grp_local[r]))
+                               np.asarray(val, np.float32)[idx]))
     return plans
 
 
 # --------------------------------------------------------------------------------------------
 # device-side execution
 # --------------------------------------------------------------------------------------------
+class ShardedOperator:
+    """This rank's rows of one shift operator ([own | halo] columns) + its halo exchange plan."""
+
+    def __init__(self, plan: ShardPlan, device, F: int, rbu_mode: str = "auto"):
+        self.plan = plan
+        csr = ops.Csr(torch.from_numpy(plan.rowptr).to(device), torch.from_numpy(plan.col).to(device),
+                      torch.from_numpy(plan.val).to(device), plan.n_own)
+        self.op = ShiftOperator(csr, None, n_split=plan.n_own, n_cols=plan.n_own + plan.n_halo)
+        self.op.maybe_build_rbu(F, rbu_mode)
+        self.send_index = torch.from_numpy(plan.send_index).to(device)
+        self.send_splits = [int(c) for c in plan.send_counts]
+        self.recv_splits = [int(c) for c in plan.recv_counts]
+
+    @property
+    def n_send(self) -> int:
+        return int(self.send_index.numel())
+
+
+class _Phase:
+    """CUDA-event pairs per phase name, on whatever stream is current (bench breakdown)."""
+
+    def __init__(self):
+        self.pairs: Dict[str, list] = {}
+
+    def __call__(self, name):
+        return _PhaseCtx(self, name)
+
+    def totals_ms(self) -> Dict[str, float]:
+        return {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in self.pairs.items()}
+
+
+class _PhaseCtx:
+    def __init__(self, owner, name):
+        self.owner, self.name = owner, name
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+
+    def __exit__(self, *exc):
+        b = torch.cuda.Event(enable_timing=True)
+        b.record()
+        self.owner.pairs.setdefault(self.name, []).append((self.a, b))
+
+
+class _NoPhase:
+    def __call__(self, name):
+        return self
+
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return None
+
+
 class RowShardedEncoder:
     """Runs an :class:`sgp_b200.SGPEncoder` on this rank's rows of the graph."""
 
-    def __init__(self, encoder, edge_index, edge_weight, num_nodes: int, device, group=None,
-                 R: int = 16):
+    N_SLOTS = 3
+
+    def __init__(self, encoder, edge_index, edge_weight, num_nodes: int, device, group=None):
         self.enc, self.group, self.dev = encoder, group, torch.device(device)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         spat = encoder.sgp_encoder
-        if spat.bidirectional or spat.undirected:
-            raise NotImplementedError("row sharding currently covers the directed D^-1 A operator")
-        from .preprocessing import build_operator
-        full = build_operator(edge_index, edge_weight, num_nodes, set_diag=spat.add_self_loops,
-                              device=self.dev)
-        rowptr, col, val = (a.cpu().numpy() for a in full.csr_arrays())
-        self.plan = build_plans(rowptr, col, val, num_nodes, self.world, R, ranks=[self.rank])[0]
-        del full
-        pl = self.plan
-        csr = ops.Csr(torch.from_numpy(pl.rowptr).to(self.dev), torch.from_numpy(pl.col).to(self.dev),
-                      torch.from_numpy(pl.val).to(self.dev), pl.n_own)
+        if spat.undirected:
+            assert spat.bidirectional is False
         F = encoder.reservoir.num_layers * encoder.reservoir.hidden_size
-        self.op = ShiftOperator(csr, None, n_split=pl.n_own, n_cols=pl.n_own + pl.n_halo)
-        if spat.rbu_mode in ("force16",) and F % 128 == 0:
-            self.op.rbu = ops.rbu_build(csr, R, grp_rows_h=pl.grp_rows, n_cols=pl.n_own + pl.n_halo)
-        else:
-            self.op.maybe_build_rbu(F, spat.rbu_mode)
-        self.send_index = torch.from_numpy(pl.send_index).to(self.dev)
-        self.send_splits = [int(c) for c in pl.send_counts]
-        self.recv_splits = [int(c) for c in pl.recv_counts]
         self.F = F
-        self.streams = [torch.cuda.Stream(self.dev) for _ in range(2)]
+        # the full operators, exactly as SGPSpatialEncoder builds them (make_operators), then cut
+        full = build_operator(edge_index, edge_weight, num_nodes, gcn_norm=spat.undirected,
+                              set_diag=spat.add_self_loops, symmetrize=spat.undirected, device=self.dev)
+        rowptr, col, val = (a.cpu().numpy() for a in full.csr_arrays())
+        del full
+        self.owner = partition_rows(rowptr, col, num_nodes, self.world)
+        self.plan = build_plans(rowptr, col, val, num_nodes, self.world, ranks=[self.rank],
+                                owner=self.owner)[0]
+        self.fwd = ShardedOperator(self.plan, self.dev, F, spat.rbu_mode)
+        self.bwd: Optional[ShardedOperator] = None
+        if spat.bidirectional:
+            rev = build_operator(edge_index, edge_weight, num_nodes, gcn_norm=False,
+                                 set_diag=spat.add_self_loops, transpose=True, device=self.dev)
+            rowptr, col, val = (a.cpu().numpy() for a in rev.csr_arrays())
+            del rev
+            plan_b = build_plans(rowptr, col, val, num_nodes, self.world, ranks=[self.rank],
+                                 owner=self.owner)[0]
+            assert np.array_equal(plan_b.own, self.plan.own)
+            self.bwd = ShardedOperator(plan_b, self.dev, F, spat.rbu_mode)
+        self.op = self.fwd.op                                   # kept: the forward operator
+        self.s_scan = torch.cuda.Stream(self.dev)
+        self.s_hop = [torch.cuda.Stream(self.dev) for _ in range(2)]
 
     @property
     def own(self) -> np.ndarray:
         return self.plan.own
 
-    def _exchange(self, block: torch.Tensor, send_flat: torch.Tensor, halo_flat: torch.Tensor):
+    @property
+    def operators(self) -> List[ShardedOperator]:
+        return [o for o in (self.fwd, self.bwd) if o is not None]
+
+    def halo_rows(self) -> int:
+        return sum(o.plan.n_halo for o in self.operators)
+
+    def _exchange(self, sop: ShardedOperator, block: torch.Tensor, send_flat: torch.Tensor,
+                  halo_flat: torch.Tensor, phase):
         """Pack the rows other ranks need from `block` [Tc, n_own, F] and all-to-all them; returns
         the halo view [Tc, n_halo, F] (node-major storage, so every peer's segment is contiguous)."""
         Tc, _, F = block.shape
-        n_send, n_halo = int(self.send_index.numel()), self.plan.n_halo
+        n_send, n_halo = sop.n_send, sop.plan.n_halo
         send = send_flat[: n_send * Tc * F].view(n_send, Tc, F)
         halo = halo_flat[: n_halo * Tc * F].view(n_halo, Tc, F)
-        if n_send:
-            ops.gather_rows(block, self.send_index, send.permute(1, 0, 2))
+        with phase("pack"):
+            if n_send:
+                ops.gather_rows(block, sop.send_index, send.permute(1, 0, 2))
         per = Tc * F
-        dist.all_to_all_single(halo.view(-1), send.view(-1), [c * per for c in self.recv_splits],
-                               [c * per for c in self.send_splits], group=self.group)
+        with phase("exchange"):
+            dist.all_to_all_single(halo.view(-1), send.view(-1), [c * per for c in sop.recv_splits],
+                                   [c * per for c in sop.send_splits], group=self.group)
         return halo.permute(1, 0, 2)
 
-    def encode_stream(self, x_own: torch.Tensor, sink: Callable[[int, int, torch.Tensor], None],
-                      chunk_steps: int = 16) -> None:
+    def encode_stream(self, x_own: torch.Tensor, sink: Optional[Callable[[int, int, torch.Tensor], None]],
+                      chunk_steps: int = 16, checksum: Optional[torch.Tensor] = None,
+                      breakdown: Optional[dict] = None) -> None:
         """x_own [T, n_own, Fin] (this rank's columns of the input, host or device).  `sink`
-        receives each finished [t1-t0, n_own, D] device chunk on the stream it was produced on."""
+        receives each finished [t1-t0, n_own, D] device chunk on the stream it was produced on
+        (may be None when only `checksum` — a device float64 scalar that receives the sum of the
+        rank's whole output, accumulated by the producing kernels — is wanted).  `breakdown`, when
+        given, is filled with per-phase stream-busy milliseconds (CUDA events; phases on different
+        streams overlap, so they add up to more than the wall time)."""
         enc, pl, F, dev = self.enc, self.plan, self.F, self.dev
         res, spat = enc.reservoir, enc.sgp_encoder
         T = x_own.shape[0]
         L, H, K, D = res.num_layers, res.hidden_size, spat.receptive_field, enc.output_size
         plan = res.device_plan(dev, pl.n_own)
         state = torch.zeros(L, pl.n_own, H, device=dev)
-        step = chunk_steps
-        n_send = int(self.send_index.numel())
-        slots = []
-        for _ in range(2):
-            slots.append(dict(buf=torch.empty(step, pl.n_own, D, device=dev),
-                              send=torch.empty(max(n_send * step * F, 1), device=dev),
-                              halo=torch.empty(max(pl.n_halo * step * F, 1), device=dev),
-                              sums=torch.empty(step, F, device=dev) if spat.global_attr else None))
+        step = max(1, int(chunk_steps))
+        phase = _Phase() if breakdown is not None else _NoPhase()
+        n_send = max(o.n_send for o in self.operators)
+        n_halo = max(o.plan.n_halo for o in self.operators)
+        bufs = [torch.empty(step, pl.n_own, D, device=dev) for _ in range(self.N_SLOTS)]
+        lanes = [dict(send=torch.empty(max(n_send * step * F, 1), device=dev),
+                      halo=torch.empty(max(n_halo * step * F, 1), device=dev),
+                      sums=torch.empty(step, F, device=dev) if spat.global_attr else None)
+                 for _ in range(2)]
         main = torch.cuda.current_stream(dev)
         chunks = [(t0, min(T, t0 + step)) for t0 in range(0, T, step)]
-        for s in self.streams:
+        for s in (self.s_scan, *self.s_hop):
             s.wait_stream(main)
-        # chunks are processed in pairs: the scans are serial in time (carried state, stream 0),
-        # the hop chains of the two chunks interleave on two streams.
-        for i in range(0, len(chunks), 2):
-            pair = chunks[i:i + 2]
-            views = []
-            for j, (t0, t1) in enumerate(pair):
-                sl = slots[j]
-                with torch.cuda.stream(self.streams[0]):
-                    if j == 0:
-                        self.streams[0].wait_stream(self.streams[1])   # slot 1 / state reuse
-                    buf = sl["buf"][: t1 - t0]
-                    xc = x_own[t0:t1].detach().to(device=dev, dtype=torch.float32, non_blocking=True)
-                    res.scan_chunk(plan, xc, state, buf)
-                    views.append(buf)
-            self.streams[1].wait_stream(self.streams[0])
-            for h in range(1, K + 1):
-                for j, buf in enumerate(views):
-                    with torch.cuda.stream(self.streams[j]):
-                        src = buf[..., (h - 1) * F:h * F]
-                        halo = self._exchange(src, slots[j]["send"], slots[j]["halo"])
-                        self.op.apply(src, buf[..., h * F:(h + 1) * F], halo)
-            for j, (buf, (t0, t1)) in enumerate(zip(views, pair)):
-                with torch.cuda.stream(self.streams[j]):
-                    if spat.global_attr:
-                        sums = slots[j]["sums"][: t1 - t0]
+        slot_free: List[Optional[torch.cuda.Event]] = [None] * self.N_SLOTS
+        g = spatial_blocks(K, spat.bidirectional)
+        for c, (t0, t1) in enumerate(chunks):
+            slot, lane = c % self.N_SLOTS, c % 2
+            buf = bufs[slot][: t1 - t0]
+            # ---- scan: serial in time (carried state), its own stream ----
+            with torch.cuda.stream(self.s_scan):
+                if slot_free[slot] is not None:
+                    self.s_scan.wait_event(slot_free[slot])
+                xc = x_own[t0:t1].detach().to(device=dev, dtype=torch.float32, non_blocking=True)
+                with phase("scan"):
+                    res.scan_chunk(plan, xc, state, buf, checksum)
+                scan_done = torch.cuda.Event()
+                scan_done.record()
+            # ---- hop chains: alternate between two streams ----
+            hs = self.s_hop[lane]
+            with torch.cuda.stream(hs):
+                hs.wait_event(scan_done)
+                for sop, base in ((self.fwd, 0), (self.bwd, K)):
+                    if sop is None:
+                        continue
+                    for h in range(1, K + 1):
+                        src = buf[..., :F] if h == 1 else buf[..., (base + h - 1) * F:(base + h) * F]
+                        halo = self._exchange(sop, src, lanes[lane]["send"], lanes[lane]["halo"], phase)
+                        with phase("hop"):
+                            sop.op.apply(src, buf[..., (base + h) * F:(base + h + 1) * F], halo, checksum)
+                if spat.global_attr:
+                    with phase("global"):
+                        sums = lanes[lane]["sums"][: t1 - t0]
                         ops.node_sum(buf[..., :F], sums)
                         dist.all_reduce(sums, group=self.group)
-                        ops.node_mean_broadcast(sums, pl.num_nodes, buf[..., (K + 1) * F:(K + 2) * F])
-                    sink(t0, t1, buf)
-        for s in self.streams:
+                        ops.node_mean_broadcast(sums, pl.num_nodes, buf[..., g * F:(g + 1) * F])
+                        if checksum is not None:
+                            ops.checksum_view(buf[..., g * F:(g + 1) * F], checksum)
+                if sink is not None:
+                    with phase("sink"):
+                        sink(t0, t1, buf)
+                ev = torch.cuda.Event()
+                ev.record()
+                slot_free[slot] = ev
+        for s in (self.s_scan, *self.s_hop):
             main.wait_stream(s)
+        if breakdown is not None:
+            torch.cuda.synchronize(dev)
+            breakdown.update(phase.totals_ms())
+        self._plan_for_check = plan
+
+    def check(self) -> None:
+        """Raise on EVERY rank if a tensor-core launch of any rank reported a barrier timeout
+        (results invalid).  Synchronises the device and the group."""
+        bad = 0
+        for sop in self.operators:
+            if sop.op.tc is not None:
+                bad |= int(sop.op.tc.err.item() != 0)
+        for entry in getattr(self, "_plan_for_check", []) or []:
+            if entry[0] == "tc":
+                bad |= int(entry[-1].item() != 0)
+        flag = torch.tensor([bad], device=self.dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()) != 0:
+            raise SgpError("row-sharded encode: a tensor-core kernel reported a barrier timeout on at "
+                           "least one rank (results invalid)")
+
+
+def encode_sharded_lockstep(encoder, edge_index, edge_weight, num_nodes: int, x: torch.Tensor,
+                            world: int, device) -> torch.Tensor:
+    """Single-process, single-GPU emulation of the row-sharded encode: `world` shards are built
+    with the same plans and device kernels (halo pack, second-source SpMM) and advanced hop by hop
+    in lockstep, the all-to-all replaced by direct copies between the shards' buffers.  Returns the
+    assembled [T, N, D] output.  This is what the one-GPU parity test drives; the NCCL pipeline
+    itself is checked by tools/check_sharded.py under torchrun."""
+    dev = torch.device(device)
+    spat, res = encoder.sgp_encoder, encoder.reservoir
+    F, K, D = res.num_layers * res.hidden_size, spat.receptive_field, encoder.output_size
+    T = x.shape[0]
+    specs = [dict(gcn_norm=spat.undirected, set_diag=spat.add_self_loops, symmetrize=spat.undirected)]
+    if spat.bidirectional:
+        specs.append(dict(gcn_norm=False, set_diag=spat.add_self_loops, transpose=True))
+    owner, shards = None, []           # shards[o][r] = ShardedOperator
+    for spec in specs:
+        full = build_operator(edge_index, edge_weight, num_nodes, device=dev, **spec)
+        rowptr, col, val = (a.cpu().numpy() for a in full.csr_arrays())
+        if owner is None:
+            owner = partition_rows(rowptr, col, num_nodes, world)
+        plans = build_plans(rowptr, col, val, num_nodes, world, owner=owner)
+        shards.append([ShardedOperator(p, dev, F, spat.rbu_mode) for p in plans])
+    plans = [s.plan for s in shards[0]]
+    xs = x.detach().to(device=dev, dtype=torch.float32)
+    bufs = []
+    for p in plans:
+        buf = torch.empty(T, p.n_own, D, device=dev)
+        state = torch.zeros(res.num_layers, p.n_own, res.hidden_size, device=dev)
+        plan = res.device_plan(dev, p.n_own)
+        res.scan_chunk(plan, xs[:, torch.from_numpy(p.own).to(dev)].contiguous(), state, buf)
+        res.check_plan(plan)
+        bufs.append(buf)
+    for o, base in zip(range(len(shards)), (0, K)):
+        for h in range(1, K + 1):
+            sl = slice(0, F) if h == 1 else slice((base + h - 1) * F, (base + h) * F)
+            # pack on every shard, then "exchange": rank p's halo segment from q = q's send segment for p
+            sends = []
+            for r, sop in enumerate(shards[o]):
+                send = torch.empty(sop.n_send, T, F, device=dev)
+                if sop.n_send:
+                    ops.gather_rows(bufs[r][..., sl], sop.send_index, send.permute(1, 0, 2))
+                sends.append(send)
+            for r, sop in enumerate(shards[o]):
+                parts = []
+                for q, sq in enumerate(shards[o]):
+                    off = int(np.sum(sq.plan.send_counts[:r]))
+                    parts.append(sends[q][off:off + int(sq.plan.send_counts[r])])
+                halo = torch.cat(parts, 0) if parts else torch.empty(0, T, F, device=dev)
+                assert halo.shape[0] == sop.plan.n_halo
+                sop.op.apply(bufs[r][..., sl], bufs[r][..., (base + h) * F:(base + h + 1) * F],
+                             halo.permute(1, 0, 2))
+                sop.op.check()
+    out = torch.empty(T, num_nodes, D, device=dev)
+    if spat.global_attr:
+        g = spatial_blocks(K, spat.bidirectional)
+        total = torch.zeros(T, F, device=dev)
+        for r in range(world):
+            sums = torch.empty(T, F, device=dev)
+            ops.node_sum(bufs[r][..., :F], sums)
+            total += sums
+        for r in range(world):
+            ops.node_mean_broadcast(total, num_nodes, bufs[r][..., g * F:(g + 1) * F])
+    for r, p in enumerate(plans):
+        out[:, torch.from_numpy(p.own).to(dev)] = bufs[r]
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -231,31 +401,40 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
     """Strong scaling of the bench workload: the same N x T series, rows sharded over `world`
     GPUs.  value = N*T / max-over-ranks device time."""
     import json
+    import time
     import sgp_b200
     from . import _lib
     from .synthetic import make_graph, sensor_signal
 
     N, T, H, K, Fin = cfg["N"], cfg["T"], cfg["H"], cfg["K"], cfg["Fin"]
     ei, ew = make_graph(cfg, seed=0)
+    ei_t, ew_t = torch.from_numpy(ei), torch.from_numpy(ew)
     torch.manual_seed(2)
     enc = sgp_b200.SGPEncoder(input_size=Fin, reservoir_size=H, reservoir_layers=1, leaking_rate=0.9,
                               spectral_radius=0.9, density=0.7, input_scaling=1.0, receptive_field=K,
                               bidirectional=False, alpha_decay=False, global_attr=False)
-    sh = RowShardedEncoder(enc, torch.from_numpy(ei), torch.from_numpy(ew), N, dev)
+    torch.cuda.synchronize()
+    t_b0 = time.perf_counter()
+    sh = RowShardedEncoder(enc, ei_t, ew_t, N, dev)
+    torch.cuda.synchronize()
+    build_ms = torch.tensor([(time.perf_counter() - t_b0) * 1e3], device=dev)
+    dist.all_reduce(build_ms, op=dist.ReduceOp.MAX)
     x = sensor_signal(T, N, seed=1, exogenous=Fin == 3)
     x_host = torch.from_numpy(np.ascontiguousarray(x[:, sh.own])).pin_memory()     # this rank's rows, pinned
     x_own = x_host.to(dev)
     del x
     D = enc.output_size
-    step = args.chunk or max(1, min(T, (args.chunk_mb << 20) // max(sh.plan.n_own * D * 4, 1)))
+    # >= 32 chunks per pass so that the 3-stage pipeline has something to overlap
+    step = args.chunk or max(1, min((T + 31) // 32, (args.chunk_mb << 20) // max(sh.plan.n_own * D * 4, 1)))
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
 
-    def one_pass():
-        sh.encode_stream(x_own, lambda t0, t1, chunk: ops.checksum(chunk, acc), chunk_steps=step)
+    def one_pass(breakdown=None):
+        sh.encode_stream(x_own, None, chunk_steps=step, checksum=acc, breakdown=breakdown)
 
     for _ in range(args.warmup):
         one_pass()
     torch.cuda.synchronize()
+    sh.check()
     acc.zero_()
     sampler = clock_sampler(dev.index) if (clock_sampler is not None and rank == 0) else None
     if sampler is not None:
@@ -271,17 +450,29 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
     torch.cuda.synchronize()
     dist.barrier()
     clocks = sampler.stop() if sampler is not None else None
+    launches = torch.tensor([_lib.launch_count() - l0], device=dev)
+    sh.check()
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    chk_timed = acc.clone()
+    dist.all_reduce(chk_timed)
+    # ---- one more, instrumented pass: per-phase stream-busy time on this rank (max over ranks) ----
+    bd: dict = {}
+    one_pass(bd)
+    names = ["scan", "pack", "exchange", "hop", "global", "sink"]
+    bd_t = torch.tensor([bd.get(k, 0.0) for k in names], device=dev, dtype=torch.float64)
+    bd_max, bd_sum = bd_t.clone(), bd_t.clone()
+    dist.all_reduce(bd_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(bd_sum)
     # ---- end to end: every step copies this rank's rows of the series from pinned host memory
-    # and reads the checksum back; the operator / halo plan is built once (it is per graph)
+    # and reads the checksum back; the operator / halo plan is per graph and built once (build_ms)
     chk_dev = torch.zeros(1, dtype=torch.float64, device=dev)
     chk_host = torch.zeros(1, dtype=torch.float64).pin_memory()
 
     def one_pass_e2e():
         xd = x_host.to(dev, non_blocking=True)
         chk_dev.zero_()
-        sh.encode_stream(xd, lambda t0, t1, chunk: ops.checksum(chunk, chk_dev), chunk_steps=step)
+        sh.encode_stream(xd, None, chunk_steps=step, checksum=chk_dev)
         chk_host.copy_(chk_dev, non_blocking=True)
 
     one_pass_e2e()
@@ -295,30 +486,48 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
     f1.record()
     torch.cuda.synchronize()
     dist.barrier()
+    sh.check()
     ms_e2e = torch.tensor([f0.elapsed_time(f1) / n_e2e], device=dev)
     dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     h2d = torch.tensor([float(x_host.numel() * 4)], device=dev, dtype=torch.float64)
     dist.all_reduce(h2d)
-    launches = torch.tensor([_lib.launch_count() - l0], device=dev)
     dist.all_reduce(launches)
-    halo = torch.tensor([sh.plan.n_halo, sh.plan.n_own], device=dev, dtype=torch.float64)
+    halo = torch.tensor([sh.halo_rows(), sh.plan.n_own], device=dev, dtype=torch.float64)
     dist.all_reduce(halo)
-    dist.all_reduce(acc)
+    chk_e2e = torch.tensor([float(chk_host)], device=dev, dtype=torch.float64)
+    dist.all_reduce(chk_e2e)
     if rank == 0:
         ms_step = float(ms)
         value = N * T / (ms_step * 1e-3)
+        fmt = sh.fwd.op
+        nvlink_bytes = float(halo[0]) * 4 * H * K * T          # halo rows x row bytes x hops x time steps
         line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f32", data="synthetic",
-                    config=config_dict(cfg, world, extra=dict(
+                    config=config_dict(cfg, world),
+                    kernel_config=dict(
                         chunk_steps=step, halo_rows_per_owned_row=float(halo[0] / halo[1]),
-                        exchange="all_to_all_v of halo rows per hop (NCCL), 2 chunks in flight")),
-                    roofline=None, cpu_baseline=None,
+                        operator_format=("tcgen05 64-row groups" if fmt.tc is not None else
+                                         "rbu%d" % fmt.rbu.R if fmt.rbu is not None else "csr"),
+                        partition="recursive bisection along the patch diameter (sgp_partition_rows)",
+                        exchange="all_to_all_v of halo rows per hop (NCCL); scan / 2 hop chains on 3 streams, "
+                                 "3 chunk buffers",
+                        sink="fp64 checksum of the whole output, accumulated in the scan / hop epilogues"),
+                    roofline=None,
+                    breakdown=dict(
+                        unit="ms of stream-busy time per pass, CUDA events on the phase's own stream; phases on "
+                             "different streams overlap (sum > ms_per_step); 'exchange' includes waiting for peers",
+                        max_over_ranks={k: float(v) for k, v in zip(names, bd_max)},
+                        mean_over_ranks={k: float(v) / world for k, v in zip(names, bd_sum)},
+                        nvlink_bytes_received_per_pass_all_ranks=nvlink_bytes,
+                        operator_build_ms_max_over_ranks=float(build_ms)),
+                    cpu_baseline=None,
                     e2e=dict(value=N * T / (float(ms_e2e) * 1e-3), unit=unit, h2d_bytes_per_step=int(h2d),
-                             d2h_bytes_per_step=8 * world, ms_per_step=float(ms_e2e), checksum=float(chk_host),
+                             d2h_bytes_per_step=8 * world, ms_per_step=float(ms_e2e), checksum=float(chk_e2e),
                              note="per step every rank copies its rows of x from pinned host memory, encodes "
-                                  "(scan + halo exchange + K hops per chunk) and reads its checksum back; the "
-                                  "operator and halo plan are per graph and built once, outside the step"),
-                    clocks=clocks, gpu_launches=int(launches), checksum=float(acc) / args.steps)
+                                  "(scan + halo exchange + K hops per chunk, checksum fused into the kernels' "
+                                  "epilogues) and reads its checksum back; the operator and halo plan are per "
+                                  "graph, built once outside the step (operator_build_ms) — as in the 1-GPU line"),
+                    clocks=clocks, gpu_launches=int(launches), checksum=float(chk_timed) / args.steps)
         print(json.dumps(line))
     dist.destroy_process_group()

@@ -471,3 +471,228 @@ def test_temporal_encoder_and_reservoir_module_api():
     assert_blocks_close(yb[0].numpy(), g["y"], kw["hidden_size"])
     last = enc.reservoir(xb, return_last_state=True)
     np.testing.assert_array_equal(last.numpy(), yb[:, -1].numpy())
+
+
+# ---------------------------------------------------------------- BASELINE shapes through the public API
+def _layers_of(enc):
+    return [dict(w_ih=l.w_ih.data, w_hh=l.w_hh.data, b_ih=l.b_ih.data, alpha=l.alpha)
+            for l in enc.reservoir.reservoir_layers]
+
+
+BASELINE_CASES = [
+    # BASELINE.json configs[1..4] at reduced T (full N / graph / H / K), plus a bidirectional +
+    # global-attribute case at tensor-core shapes.  `tc` = auto-dispatch must pick the tcgen05 scan
+    # AND the tcgen05 hop (N >= 2048, nnz >= 200k, F in {128, 256, 512}).
+    dict(name="c2_pems_bay", N=325, k=8, H=128, K=4, T=64, Fin=3, tc=False),
+    dict(name="c3_pv_us", N=5016, k=100, H=256, K=4, T=8, Fin=3, tc=True),
+    dict(name="c4_100k", N=100_000, k=100, H=256, K=4, T=2, Fin=1, tc=True),
+    dict(name="c5_1m", N=1_000_000, k=32, H=128, K=2, T=2, Fin=1, tc=True),
+    dict(name="bidir_global_tc", N=3000, k=80, H=128, K=2, T=6, Fin=3, tc=True, bidir=True, glob=True),
+    dict(name="undirected_loops_tc", N=2600, k=90, H=128, K=2, T=5, Fin=3, tc=True, undirected=True, loops=True),
+]
+
+
+@pytest.mark.parametrize("c", BASELINE_CASES, ids=lambda c: c["name"])
+def test_sgp_encoder_baseline_shapes_vs_oracle(c):
+    """SGPEncoder.forward (host tensors in, host tensor out: the reference's call) at the BASELINE
+    shapes with the library's own kernel dispatch, against the float64 reservoir oracle + the C
+    SpMM oracle."""
+    N, T, H, K, Fin = c["N"], c["T"], c["H"], c["K"], c["Fin"]
+    bidir, glob, und, loops = (c.get(k, False) for k in ("bidir", "glob", "undirected", "loops"))
+    ei, ew = sensor_knn(N, c["k"], seed=0)
+    x = sensor_signal(T, N, seed=1, exogenous=Fin == 3)
+    torch.manual_seed(2)
+    enc = sgp_b200.SGPEncoder(input_size=Fin, reservoir_size=H, reservoir_layers=1, leaking_rate=0.9,
+                              spectral_radius=0.9, density=0.7, input_scaling=1.0, receptive_field=K,
+                              bidirectional=bidir, alpha_decay=False, global_attr=glob,
+                              add_self_loops=loops, undirected=und)
+    y = enc(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ew))
+    assert y.device.type == "cpu" and y.shape == (T, N, enc.output_size)
+    # which kernels the dispatch picks for this shape (deterministic: same calls as forward makes)
+    fwd, bwd = enc.sgp_encoder.build_operators(torch.from_numpy(ei), torch.from_numpy(ew), N, torch.device(DEV), H)
+    plan = enc.reservoir.device_plan(torch.device(DEV), N)
+    assert (fwd.tc is not None) == c["tc"] and (plan[0][0] == "tc") == c["tc"]
+    assert (bwd is not None) == bidir and (bwd is None or (bwd.tc is not None) == c["tc"])
+    del fwd, bwd, plan
+    ref = O.sgp_encoder(x, ei, ew, _layers_of(enc), "tanh", K, bidir, und, glob, add_self_loops=loops,
+                        impl="c", dtype=torch.float64)
+    assert_blocks_close(y.numpy(), ref, H)
+
+
+def test_fused_checksum_equals_sum_of_output():
+    """encode_stream(checksum=...) — the streaming benchmark's sink, accumulated in the scan / hop
+    epilogues — against the fp64 sum of the materialised output, on the tcgen05 path and on the
+    CUDA-core path (global block included)."""
+    for N, k, H, K, glob, mode in [(2304, 100, 128, 2, True, "auto"), (300, 8, 64, 3, True, "auto"),
+                                   (2304, 30, 256, 1, False, "force16")]:
+        ei, ew = sensor_knn(N, k, seed=3)
+        x = torch.from_numpy(sensor_signal(13, N, seed=2))
+        torch.manual_seed(5)
+        enc = sgp_b200.SGPEncoder(3, H, 1, 0.9, 0.9, 0.7, 1.0, K, False, False, glob)
+        enc.sgp_encoder.rbu_mode = mode
+        enc.chunk_steps = 5
+        acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+        total = torch.zeros(1, dtype=torch.float64, device=DEV)
+
+        def sink(t0, t1, chunk):
+            total.add_(chunk.double().sum())
+
+        enc.encode_stream(x, torch.from_numpy(ei), torch.from_numpy(ew), sink, checksum=acc)
+        assert abs(float(acc) - float(total)) <= 1e-9 * 13 * N * enc.output_size + 1e-7 * abs(float(total))
+        acc2 = torch.zeros(1, dtype=torch.float64, device=DEV)
+        enc.encode_stream(x, torch.from_numpy(ei), torch.from_numpy(ew), None, checksum=acc2)   # sink-less run
+        assert abs(float(acc2) - float(acc)) <= 1e-9 * abs(float(acc)) + 1e-9
+
+
+def test_spmm_tensor_core_row_offsets_beyond_4gb():
+    """Source rows x row stride > 2^32 bytes (the reference's hyper-parameter grid reaches it: N = 1M
+    with D >= 1074 floats): gathered-row offsets are formed in 64 bits."""
+    n, k, F, stride = 70_000, 6, 128, 16_384                       # 70k rows x 64 KB = 4.6 GB
+    ei, ew = sensor_knn(n, k, seed=9)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    tc = ops.tc_build(op.csr)
+    big = torch.empty(1, n, stride, device=DEV)
+    src = big[..., :F]
+    src.copy_(torch.randn(1, n, F, device=DEV))
+    a, b = torch.empty(1, n, F, device=DEV), torch.empty(1, n, F, device=DEV)
+    ops.spmm_tc(tc, src, a)
+    ops.tc_check(tc)
+    ops.spmm(op.csr, src, b)
+    assert float((a - b).abs().max()) < 2e-5 * float(b.abs().max())
+    # and with the far rows addressed through the halo source (bit 31 of the in-kernel row id)
+    n_own = 1000
+    rp, cl, vl = op.csr.rowptr[:n_own + 1], op.csr.col[:int(op.csr.rowptr[n_own])], op.csr.val[:int(op.csr.rowptr[n_own])]
+    tc2 = ops.tc_build(ops.Csr(rp.contiguous(), cl.contiguous(), vl.contiguous(), n_own), n_cols=n)
+    a2 = torch.empty(1, n_own, F, device=DEV)
+    ops.spmm_tc(tc2, src[:, :n_own], a2, halo=src[:, n_own:], n_split=n_own)
+    ops.tc_check(tc2)
+    assert float((a2 - b[:, :n_own]).abs().max()) < 2e-5 * float(b.abs().max())
+
+
+def test_spmm_rbu_wide_features_and_gather_paths():
+    """F = 640 (five 128-column chunks: two launches over feature slices) and both gather paths."""
+    n = 1203
+    ei, ew = sensor_knn(n, 20, seed=1)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    rbu = ops.rbu_build(op.csr, 16)
+    x = torch.randn(2, n, 640, device=DEV)
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    ops.spmm_rbu(rbu, x, a)
+    ops.spmm(op.csr, x, b)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    idx = torch.tensor([4, 4, 49, 0, 17], dtype=torch.int32, device=DEV)
+    for F in (7, 12, 256):                                          # scalar path, vector path
+        src = torch.randn(3, 50, F, device=DEV)
+        dst = torch.empty(5, 3, F, device=DEV).permute(1, 0, 2)     # node-major destination, as the exchange uses
+        ops.gather_rows(src, idx, dst)
+        assert torch.equal(dst, src[:, idx.long()])
+    v = torch.randn(3, 77, 300, device=DEV)[..., 20:120]
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.checksum_view(v, acc)
+    assert abs(float(acc) - float(v.double().sum())) < 1e-6
+
+
+# ---------------------------------------------------------------- row-sharded path on one GPU
+@pytest.mark.parametrize("world,kw", [(2, dict()), (3, dict(bidir=True, glob=True)),
+                                      (4, dict(undirected=True, loops=True, glob=True))])
+def test_row_sharded_lockstep_equals_single_gpu(world, kw):
+    """The sharded encoder's plans and device kernels (halo pack, second-source tensor-core SpMM,
+    per-operator halo plans of the bidirectional / undirected encoders) on ONE GPU: `world` shards
+    advanced in lockstep with the all-to-all replaced by copies, against the unsharded encoder."""
+    from sgp_b200.sharded import encode_sharded_lockstep
+    N, k, T, H, K = 3000, 90, 7, 128, 2
+    ei, ew = sensor_knn(N, k, seed=0)
+    x = torch.from_numpy(sensor_signal(T, N, seed=1))
+    torch.manual_seed(2)
+    enc = sgp_b200.SGPEncoder(3, H, 1, 0.9, 0.9, 0.7, 1.0, K, kw.get("bidir", False), False,
+                              kw.get("glob", False), add_self_loops=kw.get("loops", False),
+                              undirected=kw.get("undirected", False))
+    enc.sgp_encoder.rbu_mode = "tc"
+    full = enc(x.to(DEV), torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV))
+    got = encode_sharded_lockstep(enc, torch.from_numpy(ei), torch.from_numpy(ew), N, x, world, DEV)
+    err = float((got - full).abs().max() / full.abs().max())
+    assert err < 5e-6, err
+    ref = O.sgp_encoder(x.numpy(), ei, ew, _layers_of(enc), "tanh", K, kw.get("bidir", False),
+                        kw.get("undirected", False), kw.get("glob", False),
+                        add_self_loops=kw.get("loops", False), impl="c", dtype=torch.float64)
+    assert_blocks_close(got.cpu().numpy(), ref, H)
+
+
+# ---------------------------------------------------------------- a9 / a10: the dataset-level callers
+class _DatasetStub:
+    """Duck-typed stand-in for tsl's SpatioTemporalDataset: exactly the surface lib/utils.py:10-47
+    and lib/sgp_preprocessing.py:15-37 touch."""
+
+    def __init__(self, data, exog, edge_index, edge_weight):
+        self.data, self.exogenous = data, dict(exog)
+        self.edge_index, self.edge_weight = edge_index, edge_weight
+        self.input_map = None
+
+    def get_tensors(self, keys, preprocess=False, cat_dim=None):
+        ts = [self.data if k == "data" else self.exogenous[k] for k in keys]
+        return (torch.cat(ts, cat_dim) if cat_dim is not None else ts), None
+
+    def add_exogenous(self, name, value, add_to_input_map=True):
+        assert value.shape[0] == self.data.shape[0] and value.shape[1] == self.data.shape[1]
+        self.exogenous[name] = value.clone().float()
+
+    def set_input_map(self, m):
+        self.input_map = dict(m)
+
+
+def _stub_dataset(N=150, T=30):
+    ei, ew = sensor_thresh(N, 6 * N, seed=4)
+    x = sensor_signal(T, N, seed=3)
+    ds = _DatasetStub(torch.from_numpy(x[..., :1].copy()), {"u": torch.from_numpy(x[..., 1:].copy())},
+                      torch.from_numpy(ei), torch.from_numpy(ew))
+    return ds, x, ei, ew
+
+
+@pytest.mark.parametrize("encode_exog,keep_raw", [(True, False), (False, True)])
+def test_encode_dataset_happy_path(tmp_path, encode_exog, keep_raw):
+    """lib/utils.py:10-47: get_tensors -> encoder -> add_exogenous('encoded_x') -> set_input_map."""
+    ds, x, ei, ew = _stub_dataset()
+    Fin = 3 if encode_exog else 1
+    kwargs = dict(input_size=Fin, reservoir_size=32, reservoir_layers=2, leaking_rate=0.8, spectral_radius=0.9,
+                  density=0.7, input_scaling=1.0, receptive_field=2, bidirectional=True, alpha_decay=True,
+                  global_attr=True)
+    torch.manual_seed(7)
+    path = tmp_path / "enc.pt"
+    out = sgp_b200.encode_dataset(ds, sgp_b200.SGPEncoder, kwargs, encode_exogenous=encode_exog,
+                                  keep_raw=keep_raw, save_path=str(path))
+    assert out is ds and "encoded_x" in ds.exogenous
+    want_map = {"x": ["encoded_x"]}
+    if not encode_exog or keep_raw:
+        want_map["u"] = ([] if encode_exog else ["u"]) + (["data"] if keep_raw else [])
+    assert ds.input_map == want_map
+    torch.manual_seed(7)
+    layers = O.draw_reservoir(Fin, 32, 2, 0.8, 0.9, 0.7, 1.0, alpha_decay=True)
+    ref = O.sgp_encoder(x[..., :Fin], ei, ew, layers, "tanh", 2, True, False, True, impl="c", dtype=torch.float64)
+    y = ds.exogenous["encoded_x"]
+    assert y.device.type == "cpu" and y.shape == ref.shape
+    assert_blocks_close(y.numpy(), ref, 64)
+    assert torch.equal(torch.load(str(path)), y)
+
+
+def test_preprocess_dataset_and_reservoir_preprocessing():
+    """lib/sgp_preprocessing.py:15-64: the functional twins (reservoir states, then the spatial
+    embedding list concatenated into exogenous 'processed_x')."""
+    ds, x, ei, ew = _stub_dataset(N=120, T=25)
+    rk = dict(hidden_size=48, num_layers=2, leaking_rate=0.9, spectral_radius=0.9, density=0.8)
+    sk = dict(k=3, bidirectional=True, add_self_loops=True)
+    torch.manual_seed(11)
+    sgp_b200.preprocess_dataset(ds, True, rk, sk)
+    assert ds.input_map == {"x": ["processed_x"]}
+    torch.manual_seed(11)
+    layers = O.draw_reservoir(3, 48, 2, 0.9, 0.9, 0.8, 1.0)
+    h = O.reservoir_states(x, layers, "tanh", dtype=torch.float64).numpy().astype(np.float32)
+    ref = np.concatenate(O.spatial_embedding(h, 120, ei, ew, k=3, bidirectional=True, add_self_loops=True,
+                                             impl="c"), -1)
+    y = ds.exogenous["processed_x"]
+    assert y.shape == ref.shape == (25, 120, 7 * 96)
+    assert_blocks_close(y.numpy(), ref, 96)
+    # reservoir_preprocessing_ alone, data on the host, `cuda` flag accepted
+    torch.manual_seed(11)
+    r = sgp_b200.reservoir_preprocessing_(torch.from_numpy(x), cuda=True, **rk)
+    assert r.device.type == "cpu"
+    assert_blocks_close(r.numpy(), h, 48)

@@ -169,3 +169,74 @@ def test_encoder_composition_layer_major():
 def test_bad_edge_index_type():
     with pytest.raises(RuntimeError):
         O.build_operator([[0], [1]], None, 2)
+
+
+# ---- every flag combination against two independent sparse libraries -----------------------
+# torch_sparse / PyG cannot be installed here (parity of the spatial path stays "unpinned"), so the
+# restatement of their semantics is cross-checked, for EVERY flag combination the product builds,
+# against a dense float64 construction written straight from the reference's source lines and
+# against scipy.sparse and torch.sparse_csr matmuls of the oracle's CSR.
+ALL_FLAG_CASES = [dict(gcn_norm=g, set_diag=s, remove_diag=r, symmetrize=u, transpose=t)
+                  for g in (False, True) for s in (False, True) for r in (False, True)
+                  for u in (False, True) for t in (False, True)
+                  if not (u and t) and (g == u)]      # the callers' combinations (:182-192, :205-216)
+
+
+def _dense_reference(ei, ew, n, gcn_norm, set_diag, remove_diag, symmetrize, transpose):
+    """float64 dense restatement of lib/sgp_preprocessing.py:67-105 (+ :182-185, :205-207)."""
+    ei = np.asarray(ei)
+    if transpose:
+        ei = ei[[1, 0]]
+    w = np.ones(ei.shape[1]) if ew is None else np.asarray(ew, np.float64)
+    A = np.zeros((n, n))
+    if symmetrize:                                   # to_undirected: both directions, coalesced by add
+        np.add.at(A, (ei[0], ei[1]), w)
+        np.add.at(A, (ei[1], ei[0]), w)
+        if ew is None:                               # no attribute to add: coalesce only de-duplicates
+            A = (A > 0).astype(np.float64)
+        A = A.T                                      # then col, row = edge_index
+    else:
+        np.add.at(A, (ei[1], ei[0]), w)              # row = edge_index[1], col = edge_index[0]; duplicates add
+    if set_diag:
+        np.fill_diagonal(A, 1.0)
+    elif remove_diag:
+        np.fill_diagonal(A, 0.0)
+    deg = A.sum(1)
+    with np.errstate(divide="ignore"):
+        if gcn_norm:
+            d = deg ** -0.5
+            d[np.isinf(d)] = 0
+            return d[:, None] * A * d[None, :]
+        d = deg ** -1.0
+        d[np.isinf(d)] = 0
+        return d[:, None] * A
+
+
+@pytest.mark.parametrize("flags", ALL_FLAG_CASES, ids=lambda f: "-".join(k for k, v in f.items() if v) or "plain")
+@pytest.mark.parametrize("weighted", [True, False])
+def test_operator_all_flags_vs_dense_scipy_and_torch_sparse(flags, weighted):
+    import scipy.sparse as sp
+    n = 37
+    g = np.random.default_rng(11)
+    ei = g.integers(0, n, size=(2, 260)).astype(np.int64)
+    ei = ei[:, ei[1] != 5]                                        # an empty row (degree 0 -> zero row)
+    ei[:, :6] = np.array([[3, 3, 3, 7, 7, 9], [9, 9, 9, 7, 7, 3]])   # duplicates, a stored diagonal, a 2-cycle
+    ew = g.uniform(0.1, 1.0, size=ei.shape[1]).astype(np.float32) if weighted else None
+    e2, w2 = ei, ew
+    if flags["transpose"]:
+        e2 = e2[[1, 0]]
+    if flags["symmetrize"]:
+        e2, w2 = O.undirected_edges(e2, w2, n)
+    rowptr, col, val = O.build_operator(e2, w2, n, gcn_norm=flags["gcn_norm"], set_diag=flags["set_diag"],
+                                        remove_diag=flags["remove_diag"])
+    want = _dense_reference(ei, ew, n, **flags)
+    np.testing.assert_allclose(O.csr_to_dense(rowptr, col, val, n), want, rtol=2e-6, atol=1e-7)
+    assert np.all(np.diff(col.astype(np.int64) + n * np.repeat(np.arange(n), np.diff(rowptr))) >= 0)   # (row, col) order
+    x = g.standard_normal((n, 6)).astype(np.float32)
+    S = sp.csr_matrix((val, col, rowptr), shape=(n, n))
+    St = torch.sparse_csr_tensor(torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(val), (n, n),
+                                 check_invariants=False)      # duplicates are kept (torch_sparse semantics)
+    y_np = want @ x.astype(np.float64)
+    for got in (S @ x, (St @ torch.from_numpy(x)).numpy(), O.spmm_loops(rowptr, col, val, x[None])[0],
+                O.spmm(rowptr, col, val, x[None], impl="c")[0]):
+        np.testing.assert_allclose(got, y_np, rtol=1e-5, atol=1e-6)
