@@ -264,7 +264,8 @@ def run_own(args, cfg):
     F, D = H, (K + 1) * H
     ei, ew, x = make_inputs(cfg)
     enc = make_encoder(cfg)
-    enc.chunk_steps = args.chunk or max(1, min(T, (args.chunk_mb << 20) // (N * D * 4)))
+    from sgp_b200.preprocessing import round_chunk_steps
+    enc.chunk_steps = args.chunk or round_chunk_steps((args.chunk_mb << 20) // (N * D * 4), T)
     step_T = enc.chunk_steps
 
     # ---- resident inputs for the device-timed number ---------------------------------------

@@ -51,6 +51,7 @@ extern "C" {
 #define SGP_CSR_GCN_NORM 4     /* D^-1/2 S D^-1/2 instead of D^-1 S */
 #define SGP_CSR_SYMMETRIZE 8   /* to_undirected(): add reversed edges, coalesce duplicates by add */
 #define SGP_CSR_TRANSPOSE 16   /* swap the two rows of edge_index first (the bidirectional pass) */
+#define SGP_CSR_NO_NORM 32     /* keep the weights as given (an already normalised adjacency: GESNLayer.forward) */
 
 int sgp_version(void);
 const char* sgp_last_error(void);
@@ -185,6 +186,30 @@ int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int
 int sgp_group_rows(const int32_t* rowptr, const int32_t* col, const float* val, int32_t N, int32_t R,
                    int32_t* grp_rows, int32_t* n_groups_out);
 
+/* ---------------------------------------------------------------------------------------------
+ * DynGESN layer update (lib/nn/reservoir/graph_reservoir.py:85-93), one time step, one layer:
+ *     h' = (1 - alpha) h + alpha * act( x W_ih^T + b + prop ),   prop = S (h W_hh^T)
+ * `prop` [N, H] is produced by the caller with sgp_reservoir_scan (identity, one step: h W_hh^T)
+ * and the K2 SpMM; this fuses the input projection, bias, activation and leaky blend.  h_state
+ * [N, H] contiguous in/out; out row n at out + n*out_n_stride (a feature block of the [T, N, L*H]
+ * output); bias may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int sgp_gesn_update(const float* x, int64_t x_n_stride, int Fin, const float* w_ih /*[H,Fin]*/,
+                    const float* bias /*[H] or NULL*/, const float* prop, int64_t prop_n_stride,
+                    float alpha, float one_minus_alpha, int act, float* h_state,
+                    float* out, int64_t out_n_stride, int N, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grouped 1x1 convolution (forward) — the first decoder layer over the encoder's (hop, layer)
+ * feature blocks: nn.Conv1d(groups*Cin, groups*Cout, kernel_size=1, groups=groups) on 'b f n'
+ * (lib/nn/models/sgp_model.py:41-52).  x row r at x + r*x_row_stride holds groups*Cin features,
+ * weight [groups*Cout, Cin] (the Conv1d weight with its trailing kernel dim of 1 dropped), bias
+ * [groups*Cout] or NULL, y row r at y + r*y_row_stride receives groups*Cout values.  Cout <= 256.
+ * ------------------------------------------------------------------------------------------- */
+int sgp_grouped_linear(const float* x, int64_t x_row_stride, const float* weight, const float* bias,
+                       float* y, int64_t y_row_stride, int64_t rows, int groups, int Cin, int Cout,
+                       void* stream);
+
 /* HOST function: owner[i] in [0, parts) for every row — `parts` compact, equally sized patches of
  * the graph by recursive bisection along the patch diameter (group_rows.cu).  The row-sharded
  * encoder (no counterpart in the single-process reference) gives patch r to rank r. */
@@ -210,6 +235,15 @@ int sgp_checksum(const float* buf, int64_t count, double* acc, void* stream);
 /* The same over a strided [Tc, N, F] view (a feature block of the encoder's output buffer). */
 int sgp_checksum_view(const float* src, int64_t src_t_stride, int64_t src_n_stride, int N, int F, int Tc,
                       double* acc, void* stream);
+
+/* IID (t, n) sampler gather: dst[m, 0:F] = src[t_idx[m], n_idx[m], 0:F] for m in [0, M).
+ * Replaces `tens[(step_index, None, None, node_index)]` and `tens[(hor_index, node_index[:, None], None)]`
+ * of IIDDataset.sample (lib/datasets/iid_dataset.py:57-99) for a device-resident `tens`.  The index
+ * arrays are DEVICE int64 (the reference's torch.randint dtype); out-of-range indices are the
+ * caller's responsibility (the reference would raise an IndexError on the host). */
+int sgp_gather_tn(const float* src, int64_t src_t_stride, int64_t src_n_stride, int T, int N, int F,
+                  const int64_t* t_idx, const int64_t* n_idx, int64_t M,
+                  float* dst, int64_t dst_m_stride, void* stream);
 
 /* Gather rows: dst[t, i, :] = src[t, index[i], :]  (halo packing for the row-sharded path). */
 int sgp_gather_rows(const float* src, int64_t src_t_stride, int64_t src_n_stride,

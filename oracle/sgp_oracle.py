@@ -372,3 +372,123 @@ def blockwise_allclose(got, ref, block: int, rtol: float = 1e-4, atol_rel: float
         tol = np.maximum(tol, 1e-30)
         worst = max(worst, float((np.abs(g - r) / tol).max()))
     return worst <= 1.0, worst
+
+
+# --------------------------------------------------------------------------------------
+# the callers either side of the hot path (restated for the parity tests)
+# --------------------------------------------------------------------------------------
+def iid_sample(x: np.ndarray, y: np.ndarray, step_index: np.ndarray, node_index: np.ndarray,
+               horizon: int, delay: int = 0, horizon_lag: int = 1):
+    """``IIDDataset.sample`` (lib/datasets/iid_dataset.py:57-99) for given indices:
+    ``tens[(step_index, None, None, node_index)]`` -> [B, 1, 1, D] and
+    ``tens[(hor_index, node_index[:, None], None)]`` -> [B, h, 1, C] with
+    ``hor_index = stack([step_index + i for i in range(delay + 1, horizon + 1, horizon_lag)], 1)``."""
+    xs = x[step_index, None, None, node_index]
+    hor = np.stack([step_index + i for i in range(delay + 1, horizon + 1, horizon_lag)], 1)
+    ys = y[hor, node_index[:, None], None]
+    return xs, ys
+
+
+def spatial_support_dense(edge_index, edge_weight, num_nodes: int, k: int = 2, undirected: bool = False,
+                          add_self_loops: bool = False, remove_self_loops: bool = False,
+                          bidirectional: bool = False, global_attr: bool = False, _adj=None) -> List[np.ndarray]:
+    """``sgp_spatial_support`` (lib/sgp_preprocessing.py:108-160) with dense float64 matrices, line
+    by line — including ``support.append(adj_0 @ adj_0)`` for EVERY extra order (:143-145), the
+    recursion on the assembled, un-transposed ``adj`` for ``bidirectional`` (:147-154) and the dense
+    1/N matrix for ``global_attr`` (:155-158)."""
+    N = int(num_nodes)
+    if _adj is None:
+        ei = np.asarray(edge_index, np.int64)
+        col, row = ei[0], ei[1]
+        A = np.zeros((N, N))
+        w = np.ones(ei.shape[1]) if edge_weight is None else np.asarray(edge_weight, np.float64)
+        np.add.at(A, (row, col), w)                      # SparseTensor(row, col, value): duplicates summed by @
+    else:
+        A = _adj
+    if undirected:
+        A = A + A.T
+    if add_self_loops:
+        A = A.copy()
+        np.fill_diagonal(A, 1.0)
+    elif remove_self_loops:
+        A = A.copy()
+        np.fill_diagonal(A, 0.0)
+    deg = A.sum(1)
+    with np.errstate(divide="ignore"):
+        if undirected:
+            d = deg ** -0.5
+            d[np.isinf(d)] = 0
+            A0 = d[:, None] * A * d[None, :]
+        else:
+            d = deg ** -1.0
+            d[np.isinf(d)] = 0
+            A0 = d[:, None] * A
+    support = [A0]
+    for _ in range(k - 1):
+        support.append(A0 @ A0)
+    if bidirectional:
+        support += spatial_support_dense(None, None, N, k=k, _adj=A)
+    if global_attr:
+        support.append(np.full((N, N), 1.0 / N))
+    return support
+
+
+def grouped_conv1x1(x: np.ndarray, weight: np.ndarray, bias, groups: int) -> np.ndarray:
+    """The reference's own op for SGPModel.input_encoder (lib/nn/models/sgp_model.py:41-52) on the
+    CPU, in float64: 'b n f -> b f n', conv1d(kernel_size=1, groups), 'b f n -> b n f'."""
+    xt = torch.as_tensor(x, dtype=torch.float64).permute(0, 2, 1)
+    y = torch.nn.functional.conv1d(xt, torch.as_tensor(weight, dtype=torch.float64),
+                                   None if bias is None else torch.as_tensor(bias, dtype=torch.float64),
+                                   groups=groups)
+    return y.permute(0, 2, 1).numpy()
+
+
+def gesn_operator_dense(edge_index, edge_weight, num_nodes: int) -> np.ndarray:
+    """``GESNEncoder.forward`` (lib/nn/encoders/dyn_gesn_encoder.py:34-41): PyG ``add_self_loops``
+    (unit loops appended for nodes 0..edge_index.max(), stored diagonals kept), tsl
+    ``normalize(dim=1)`` (divide by the weighted degree of ``edge_index[1]``), then
+    ``col, row = edge_index``."""
+    ei = np.asarray(edge_index, np.int64)
+    w = np.asarray(edge_weight, np.float64)
+    n_loops = int(ei.max()) + 1 if ei.size else 0
+    loops = np.arange(n_loops)
+    ei = np.concatenate([ei, np.stack([loops, loops])], 1)
+    w = np.concatenate([w, np.ones(n_loops)])
+    deg = np.zeros(num_nodes)
+    np.add.at(deg, ei[1], w)
+    w = w / deg[ei[1]]
+    S = np.zeros((num_nodes, num_nodes))
+    np.add.at(S, (ei[1], ei[0]), w)
+    return S
+
+
+def draw_graph_esn(input_size: int, hidden_size: int, num_layers: int = 1, leaking_rate: float = 0.9,
+                   spectral_radius: float = 0.9, density: float = 0.9, input_scaling: float = 1.0,
+                   alpha_decay: bool = False) -> List[dict]:
+    """``GraphESN.__init__`` (lib/nn/reservoir/graph_reservoir.py:96-144): every GESNLayer draws in its
+    constructor, then ``self.reset_parameters()`` draws all layers again; the second draw stays."""
+    draw_reservoir(input_size, hidden_size, num_layers, leaking_rate, spectral_radius, density,
+                   input_scaling, alpha_decay)
+    return draw_reservoir(input_size, hidden_size, num_layers, leaking_rate, spectral_radius, density,
+                          input_scaling, alpha_decay)
+
+
+def graph_esn_states(x, layers: Sequence[dict], S: np.ndarray, activation: str = "tanh") -> np.ndarray:
+    """``GraphESN`` over time in float64 (graph_reservoir.py:85-93 inside tsl's _GraphRNN loop,
+    tsl/nn/blocks/encoders/gcrnn.py:57-93): per step and layer
+    ``h' = (1 - a) h + a act(W_ih x + b + S (h W_hh^T))``; layer l > 0 reads layer l-1's NEW state;
+    the output concatenates all layers' states."""
+    x = torch.as_tensor(np.asarray(x), dtype=torch.float64)
+    St = torch.as_tensor(S, dtype=torch.float64)
+    T, N, _ = x.shape
+    H = layers[0]["w_hh"].shape[0]
+    h = [torch.zeros(N, H, dtype=torch.float64) for _ in layers]
+    out = torch.empty(T, N, len(layers) * H, dtype=torch.float64)
+    for t in range(T):
+        inp = x[t]
+        for i, l in enumerate(layers):
+            pre = inp @ l["w_ih"].double().t() + l["b_ih"].double() + St @ (h[i] @ l["w_hh"].double().t())
+            h[i] = (1 - float(l["alpha"])) * h[i] + float(l["alpha"]) * _activate(pre, activation)
+            inp = h[i]
+            out[t, :, i * H:(i + 1) * H] = h[i]
+    return out.numpy()

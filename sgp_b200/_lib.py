@@ -15,7 +15,7 @@ from . import _build
 
 OK = 0
 ACT_CODES = {"tanh": 0, "relu": 1, "self_norm": 2, "identity": 3}
-CSR_SET_DIAG, CSR_REMOVE_DIAG, CSR_GCN_NORM, CSR_SYMMETRIZE, CSR_TRANSPOSE = 1, 2, 4, 8, 16
+CSR_SET_DIAG, CSR_REMOVE_DIAG, CSR_GCN_NORM, CSR_SYMMETRIZE, CSR_TRANSPOSE, CSR_NO_NORM = 1, 2, 4, 8, 16, 32
 
 # name -> (restype, argtypes); must list every symbol include/sgp_b200.h declares
 SIGNATURES = {
@@ -50,12 +50,18 @@ SIGNATURES = {
                                 c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
     "sgp_group_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "sgp_gesn_update": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "sgp_grouped_linear": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                   c_int, c_void_p]),
     "sgp_partition_rows": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "sgp_node_sum": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sgp_node_mean_broadcast": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
                                         c_int, c_void_p]),
     "sgp_checksum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "sgp_checksum_view": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sgp_gather_tn": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
+                              c_void_p, c_int64, c_void_p]),
     "sgp_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64,
                                 c_int, c_int, c_void_p]),
 }

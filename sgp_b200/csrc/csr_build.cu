@@ -78,8 +78,9 @@ __global__ void csr_finalize_structure(const uint64_t* __restrict__ keys, const 
 
 // deg[i] = sum of row i (stored order); s[i] = deg^-1 or deg^-1/2 with inf -> 0
 __global__ void csr_degree_scale(const int32_t* __restrict__ rowptr, const float* __restrict__ w,
-                                 int32_t N, int gcn, int unit_w, float* __restrict__ s) {
+                                 int32_t N, int gcn, int unit_w, int no_norm, float* __restrict__ s) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        if (no_norm) { s[i] = 1.f; continue; }
         float d = 0.f;
         for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) d += unit_w ? 1.f : w[e];
         float v = gcn ? (1.0f / sqrtf(d)) : (1.0f / d);
@@ -207,9 +208,10 @@ extern "C" int sgp_csr_build(const int64_t* edge_src, const int64_t* edge_dst, c
         const int gcn = (flags & SGP_CSR_GCN_NORM) ? 1 : 0;
         // to_undirected without edge weights only de-duplicates: every distinct edge counts once
         const int unit_w = (!weight && (flags & SGP_CSR_SYMMETRIZE)) ? 1 : 0;
-        csr_degree_scale<<<grid_for(N), threads, 0, st>>>(rowptr, w, N, gcn, unit_w, scale);
+        const int no_norm = (flags & SGP_CSR_NO_NORM) ? 1 : 0;      // values stay as given (s = 1)
+        csr_degree_scale<<<grid_for(N), threads, 0, st>>>(rowptr, w, N, gcn && !no_norm, unit_w, no_norm, scale);
         SGP_LAUNCH_CHECK("csr_degree_scale");
-        csr_apply_scale<<<grid_for(P), threads, 0, st>>>(keys, w, scale, ctr, N, gcn, unit_w, val);
+        csr_apply_scale<<<grid_for(P), threads, 0, st>>>(keys, w, scale, ctr, N, gcn && !no_norm, unit_w, val);
         SGP_LAUNCH_CHECK("csr_apply_scale");
     }
     CsrCounters host{};

@@ -115,6 +115,27 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int64_t s_ts, 
     }
 }
 
+// dst[m, :] = src[t_idx[m], n_idx[m], :] — the IID (t, n) sampler's gather from the device-resident
+// encoder output (lib/datasets/iid_dataset.py:57-99: `tens[(step_index, None, None, node_index)]`).
+// One warp per sample walks the row in 512-byte pieces (16 bytes per lane) when VEC, else scalars.
+template <bool VEC>
+__global__ void gather_tn_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns, int F,
+                                 const int64_t* __restrict__ t_idx, const int64_t* __restrict__ n_idx,
+                                 int64_t M, float* __restrict__ dst, int64_t d_ms) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m = warp; m < M; m += n_warps) {
+        const float* sp = src + (size_t)__ldg(t_idx + m) * s_ts + (size_t)__ldg(n_idx + m) * s_ns;
+        float* dp = dst + (size_t)m * d_ms;
+        if (VEC) {
+            for (int f = lane; f < F / 4; f += 32) reinterpret_cast<float4*>(dp)[f] = ldg_f4_stream(sp + 4 * f);
+        } else {
+            for (int f = lane; f < F; f += 32) dp[f] = __ldg(sp + f);
+        }
+    }
+}
+
 static int grid_1d(int64_t total, int threads) {
     int64_t g = (total + threads - 1) / threads;
     const int64_t cap = (int64_t)kNumSMs * 16;
@@ -177,6 +198,26 @@ extern "C" int sgp_checksum_view(const float* src, int64_t src_t_stride, int64_t
     checksum_view_kernel<<<grid_1d(rows, rpb * 4), 256, 0, as_stream(stream)>>>(src, src_t_stride, src_n_stride,
                                                                               N, F, Tc, acc);
     SGP_LAUNCH_CHECK("checksum_view");
+    return SGP_OK;
+}
+
+extern "C" int sgp_gather_tn(const float* src, int64_t src_t_stride, int64_t src_n_stride, int T, int N, int F,
+                             const int64_t* t_idx, const int64_t* n_idx, int64_t M, float* dst,
+                             int64_t dst_m_stride, void* stream) {
+    SGP_REQUIRE(src && dst && ((t_idx && n_idx) || M == 0), SGP_EINVAL, "sgp_gather_tn: null pointer");
+    SGP_REQUIRE(T >= 0 && N >= 0 && F >= 1 && M >= 0 && dst_m_stride >= F, SGP_EINVAL,
+                "sgp_gather_tn: T=%d N=%d F=%d M=%lld", T, N, F, (long long)M);
+    if (M == 0) return SGP_OK;
+    const bool vec = F % 4 == 0 && aligned16(src) && aligned16(dst) && src_t_stride % 4 == 0 &&
+                     src_n_stride % 4 == 0 && dst_m_stride % 4 == 0;
+    const int grid = grid_1d(M, 8);                      // 8 warps (samples) per CTA of 256 threads
+    if (vec)
+        gather_tn_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, src_t_stride, src_n_stride, F, t_idx,
+                                                                   n_idx, M, dst, dst_m_stride);
+    else
+        gather_tn_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, src_t_stride, src_n_stride, F, t_idx,
+                                                                    n_idx, M, dst, dst_m_stride);
+    SGP_LAUNCH_CHECK("gather_tn");
     return SGP_OK;
 }
 

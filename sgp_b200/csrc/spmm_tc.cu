@@ -244,9 +244,16 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
     };
 
 #ifdef SGP_TC_REGDRAIN
-#define SGP_TC_FEW_REGS() asm volatile("setmaxnreg.dec.sync.aligned.u32 40;")
+    // Register re-partitioning, ONE instruction per warpgroup and before the roles diverge:
+    // setmaxnreg is .sync.aligned over the 4 warps of a warpgroup, and the last warpgroup's warps
+    // (2 issuers, slab warp, idle warp) take three different role branches below — executing the
+    // (textually identical) instruction in each branch is a different instruction per warp and
+    // hung the first hardware run.
+    // (the dec sits at the top of the branch the WHOLE last warpgroup takes, the inc at the top of the
+    // split branch: ptxas allocates each region with the count set at its head)
+#define SGP_TC_LAST_GROUP_REGS() asm volatile("setmaxnreg.dec.sync.aligned.u32 40;")
 #else
-#define SGP_TC_FEW_REGS() do { } while (0)
+#define SGP_TC_LAST_GROUP_REGS() do { } while (0)
 #endif
     // The CTA is persistent.  All barrier phases run on counters that continue across work
     // items: `it` items, `cc` chunks, (bi, bph) slab buffers, `wn` work items with at least one
@@ -582,8 +589,9 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             if (lane == 0) atomicAdd(chk, csum);
         }
 #endif
-    } else if (warp == kTcSplitWarps + kTcProducerWarps + kTcIssuers) {
-        SGP_TC_FEW_REGS();
+    } else {
+      SGP_TC_LAST_GROUP_REGS();         // issuers, slab warp (and the idle warp): one warpgroup, one branch
+      if (warp == kTcSplitWarps + kTcProducerWarps + kTcIssuers) {
         // ================= slab warp: fp32 slab image -> tf32 hi | lo images ======================
         // The operator stores each chunk's [64 rows x 32 columns] slab once, as fp32 in the K-major
         // SWIZZLE_128B layout (8 KB); splitting it here instead of at build time halves the slab
@@ -623,12 +631,9 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                 if (++bi == kTcBBufs) { bi = 0; ++bph; }
             }
         }
-#ifdef SGP_TC_REGDRAIN
-    } else if (warp >= kTcSplitWarps + kTcProducerWarps + kTcIssuers + 1) {
-        SGP_TC_FEW_REGS();              // idle warp: completes the warpgroup for setmaxnreg
-#endif
-    } else {
-        SGP_TC_FEW_REGS();
+      } else if (warp >= kTcSplitWarps + kTcProducerWarps + kTcIssuers + 1) {
+        // idle warp (register-drain builds only): completes the warpgroup for setmaxnreg
+      } else {
         // ================= MMA issuers: two warps, ONE elected thread each runs the whole loop ===
         // issuer q takes the items with (a & 1) == q: a lone thread needs ~500 cycles of
         // instruction latency per item, the tensor pipe 384
@@ -711,6 +716,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             }
         }
         __syncwarp();
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

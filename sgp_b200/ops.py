@@ -372,6 +372,49 @@ def checksum_view(view: torch.Tensor, acc: torch.Tensor) -> None:
           _stream(view.device))
 
 
+def gesn_update(x: torch.Tensor, w_ih: torch.Tensor, bias: Optional[torch.Tensor], prop: torch.Tensor,
+                alpha: float, activation: str, h_state: torch.Tensor, out: torch.Tensor) -> None:
+    """One DynGESN layer step: h' = (1-a) h + a act(x W_ih^T + b + prop); x [N, Fin], prop [N, H],
+    h_state [N, H] contiguous in/out, out [N, H] view (row stride free)."""
+    _require_cuda(x, w_ih, bias, prop, h_state, out)
+    N, Fin = x.shape
+    H = int(w_ih.shape[0])
+    assert x.stride(1) == 1 and prop.stride(1) == 1 and out.stride(1) == 1 and h_state.is_contiguous()
+    assert w_ih.is_contiguous() and prop.shape == (N, H) and out.shape == (N, H) and h_state.shape == (N, H)
+    a = float(alpha)
+    _call(x.device, "sgp_gesn_update", _p(x), x.stride(0), Fin, _p(w_ih), _p(bias), _p(prop), prop.stride(0),
+          a, float(1.0 - a), ACT_CODES[activation], _p(h_state), _p(out), out.stride(0), N, H, _stream(x.device))
+
+
+def grouped_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], groups: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[r, g*Cout + o] = b + sum_i x[r, g*Cin + i] w[g*Cout + o, i]; x [rows, groups*Cin] (row stride
+    free), weight [groups*Cout, Cin], returns [rows, groups*Cout]."""
+    _require_cuda(x, weight, bias)
+    rows, Din = x.shape
+    Cin = Din // groups
+    Cout = int(weight.shape[0]) // groups
+    assert Din == groups * Cin and weight.shape == (groups * Cout, Cin) and weight.is_contiguous() and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(rows, groups * Cout, device=x.device)
+    _call(x.device, "sgp_grouped_linear", _p(x), x.stride(0), _p(weight), _p(bias), _p(out), out.stride(0), rows,
+          groups, Cin, Cout, _stream(x.device))
+    return out
+
+
+def gather_tn(src: torch.Tensor, t_idx: torch.Tensor, n_idx: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[m, :] = src[t_idx[m], n_idx[m], :]; src a [T, N, F] view, indices device int64 [M]."""
+    _require_cuda(src, t_idx, n_idx, dst)
+    _check_view3(src, "src")
+    T, N, F = src.shape
+    M = int(t_idx.numel())
+    assert t_idx.dtype == torch.int64 and n_idx.dtype == torch.int64 and n_idx.numel() == M
+    assert t_idx.is_contiguous() and n_idx.is_contiguous()
+    assert dst.dim() == 2 and dst.shape == (M, F) and dst.dtype == torch.float32 and dst.stride(1) == 1
+    _call(src.device, "sgp_gather_tn", _p(src), src.stride(0), src.stride(1), T, N, F, _p(t_idx), _p(n_idx), M,
+          _p(dst), dst.stride(0), _stream(src.device))
+
+
 def gather_rows(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> None:
     _check_view3(src, "src")
     _check_view3(dst, "dst")

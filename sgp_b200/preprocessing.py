@@ -101,13 +101,32 @@ class ShiftOperator:
         if self.tc is not None:
             ops.tc_check(self.tc)
 
+    def index_select(self, dim: int, index: Tensor) -> "ShiftOperator":
+        """``adj.index_select(0, node_index)`` of the reference's mini-batch path
+        (lib/datasets/iid_dataset.py:113-115): the operator restricted to the rows in `index`
+        (kept in that order, repeats allowed); the result maps N source rows to len(index) rows."""
+        if dim != 0:
+            raise NotImplementedError("only row selection (dim = 0) is used by the reference")
+        dev = self.device
+        idx = torch.as_tensor(index, device=dev).to(torch.int64).reshape(-1)
+        rp = self.csr.rowptr.to(torch.int64)
+        cnt = rp[idx + 1] - rp[idx]
+        new_rp = torch.zeros(idx.numel() + 1, dtype=torch.int64, device=dev)
+        new_rp[1:] = torch.cumsum(cnt, 0)
+        total = int(new_rp[-1])
+        take = torch.repeat_interleave(rp[idx] - new_rp[:-1], cnt) + torch.arange(total, device=dev)
+        csr = ops.Csr(new_rp.to(torch.int32), self.csr.col[take].contiguous(), self.csr.val[take].contiguous(),
+                      int(idx.numel()))
+        sub = ShiftOperator(csr, None, n_split=self.n_split, n_cols=self.n_cols or self.num_nodes)
+        return sub
+
     def __matmul__(self, x: Tensor) -> Tensor:
         """``adj @ x`` for x [N, F] or [..., N, F]; result on x's device."""
         dev = self.device
         xd = x.detach().to(device=dev, dtype=torch.float32)
         lead = xd.shape[:-2]
         x3 = xd.reshape(-1, xd.size(-2), xd.size(-1)).contiguous()
-        out = torch.empty_like(x3)
+        out = torch.empty(x3.size(0), self.num_nodes, x3.size(-1), device=dev)
         self.apply(x3, out)
         return out.reshape(*lead, *out.shape[-2:]).to(x.device)
 
@@ -130,13 +149,14 @@ def _edges_to_device(edge_index, edge_weight, device):
 
 
 def build_operator(edge_index, edge_weight, num_nodes: int, *, gcn_norm=False, set_diag=False,
-                   remove_diag=False, symmetrize=False, transpose=False, device=None) -> ShiftOperator:
+                   remove_diag=False, symmetrize=False, transpose=False, normalize=True,
+                   device=None) -> ShiftOperator:
     if device is None:
         device = _cuda_device_for(edge_index if isinstance(edge_index, Tensor) else torch.empty(0))
     ei, ew = _edges_to_device(edge_index, edge_weight, device)
     flags = ((_lib.CSR_SET_DIAG if set_diag else 0) | (_lib.CSR_REMOVE_DIAG if remove_diag else 0) |
              (_lib.CSR_GCN_NORM if gcn_norm else 0) | (_lib.CSR_SYMMETRIZE if symmetrize else 0) |
-             (_lib.CSR_TRANSPOSE if transpose else 0))
+             (_lib.CSR_TRANSPOSE if transpose else 0) | (0 if normalize else _lib.CSR_NO_NORM))
     return ShiftOperator(ops.csr_build(ei, ew, int(num_nodes), flags))
 
 
@@ -213,9 +233,118 @@ def make_operators(edge_index, edge_weight, num_nodes, *, undirected, add_self_l
     return fwd, bwd
 
 
+class OperatorChain:
+    """A product of shift operators kept factored: ``(S_n .. S_1) @ x`` applies S_1 first.  Stands
+    in for the sparse-sparse product ``adj_0 @ adj_0`` of sgp_spatial_support (:143-145): the K2
+    kernels apply the factors one after the other instead of materialising S^2 (same result up to
+    fp32 rounding, no fill-in)."""
+
+    def __init__(self, factors):
+        self.factors = list(factors)             # applied left to right: factors[0] first
+
+    @property
+    def device(self):
+        return self.factors[0].device
+
+    def sparse_sizes(self):
+        return (self.factors[-1].num_nodes, self.factors[0].sparse_sizes()[1])
+
+    def __matmul__(self, x: Tensor) -> Tensor:
+        y = x.detach().to(device=self.device, dtype=torch.float32)
+        for f in self.factors:
+            y = f @ y
+        return y.to(x.device)
+
+    def index_select(self, dim: int, index: Tensor) -> "OperatorChain":
+        return OperatorChain(self.factors[:-1] + [self.factors[-1].index_select(dim, index)])
+
+
+class MeanOperator:
+    """The dense ``torch.full((N, N), 1 / N)`` support of ``global_attr`` (:155-158), never
+    materialised: ``@ x`` is the node mean broadcast to every output row (kernel K4)."""
+
+    def __init__(self, num_nodes: int, n_rows: Optional[int] = None):
+        self.num_nodes, self.n_rows = int(num_nodes), int(num_nodes if n_rows is None else n_rows)
+
+    def sparse_sizes(self):
+        return (self.n_rows, self.num_nodes)
+
+    def __matmul__(self, x: Tensor) -> Tensor:
+        dev = _cuda_device_for(x)
+        xd = x.detach().to(device=dev, dtype=torch.float32)
+        lead = xd.shape[:-2]
+        x3 = xd.reshape(-1, xd.size(-2), xd.size(-1)).contiguous()
+        sums = torch.empty(x3.size(0), x3.size(-1), device=dev)
+        ops.node_sum(x3, sums)
+        out = torch.empty(x3.size(0), self.n_rows, x3.size(-1), device=dev)
+        ops.node_mean_broadcast(sums, self.num_nodes, out)
+        return out.reshape(*lead, *out.shape[-2:]).to(x.device)
+
+    def index_select(self, dim: int, index: Tensor) -> "MeanOperator":
+        return MeanOperator(self.num_nodes, int(torch.as_tensor(index).numel()))
+
+
+def sgp_spatial_support(edge_index: Adj, edge_weight=None, num_nodes=None, k=2, undirected=False,
+                        add_self_loops=False, remove_self_loops=False, bidirectional=False,
+                        global_attr=False) -> list:
+    """Reference: lib/sgp_preprocessing.py:108-160 — the operators the on-the-fly models apply to
+    mini-batches (``SGPLoader.collate``, ``IIDDataset._populate_input_frame``).  Returns objects
+    supporting ``op @ x`` and ``op.index_select(0, node_index)`` where the reference returns
+    torch_sparse SparseTensors / a dense matrix.  Reference behaviour kept on purpose:
+
+    * the list is ``[S, S^2, S^2, ...]``: every entry after the first is ``adj_0 @ adj_0`` (:143-145),
+      never a higher power;
+    * ``bidirectional`` recurses on the assembled (un-normalised, un-transposed) adjacency with
+      every flag off (:147-154), so the "backward" operators are the row-normalised forward
+      operator again (identical to the forward list unless ``undirected`` changed the
+      normalisation);
+    * ``global_attr`` appends the N x N matrix of 1/N (:155-158), here an implicit mean operator.
+    """
+    if isinstance(edge_index, ShiftOperator):
+        raise SgpError("sgp_spatial_support needs the edge list: a built ShiftOperator is already normalised")
+    if num_nodes is None:
+        ei = torch.as_tensor(edge_index)
+        num_nodes = int(ei.max()) + 1 if ei.numel() else 0
+    dev = _cuda_device_for(edge_index if isinstance(edge_index, Tensor) else torch.empty(0))
+
+    def powers(op):
+        return [op] + [OperatorChain([op, op]) for _ in range(k - 1)]
+
+    adj_0 = build_operator(edge_index, edge_weight, num_nodes, gcn_norm=undirected, set_diag=add_self_loops,
+                           remove_diag=remove_self_loops, symmetrize=undirected, device=dev)
+    support = powers(adj_0)
+    if bidirectional:
+        back = adj_0 if not undirected else build_operator(
+            edge_index, edge_weight, num_nodes, gcn_norm=False, set_diag=add_self_loops,
+            remove_diag=remove_self_loops, symmetrize=True, device=dev)
+        support += powers(back)
+    if global_attr:
+        support.append(MeanOperator(num_nodes))
+    return support
+
+
+def sgp_collate_features(x: Tensor, support: list, node_index: Optional[Tensor] = None) -> Tensor:
+    """The feature assembly of ``SGPLoader.collate`` (lib/dataloader/sgp_dataloader.py:61-66):
+    ``cat([x] + [adj @ x for adj in support], -1)``; with ``node_index`` the row-subset form of
+    ``IIDDataset._populate_input_frame`` (lib/datasets/iid_dataset.py:112-116):
+    ``cat([x.index_select(-2, idx)] + [adj.index_select(0, idx) @ x ...], -1)``."""
+    if node_index is None:
+        return torch.cat([x] + [(adj @ x).to(x.device) for adj in support], dim=-1)
+    idx = torch.as_tensor(node_index).to(torch.int64).reshape(-1)
+    return torch.cat([x.index_select(-2, idx.to(x.device))] +
+                     [(adj.index_select(0, idx) @ x).to(x.device) for adj in support], dim=-1)
+
+
+def round_chunk_steps(steps: int, n_steps: int) -> int:
+    """Chunks of a multiple of 4 time steps: the tensor-core hop works on time blocks of 4 / (F / 128)
+    steps per work item, and a ragged last block costs a whole one (5 steps = 2 blocks of 4 at F = 128)."""
+    steps = max(1, min(int(steps), int(n_steps)))
+    return steps - steps % 4 if 4 <= steps < n_steps else steps
+
+
 def _chunk_steps(n_steps: int, bytes_per_step: int) -> int:
     budget = int(os.environ.get("SGP_B200_CHUNK_BYTES", 4 << 30))
-    return max(1, min(n_steps, budget // max(bytes_per_step, 1)))
+    return round_chunk_steps(budget // max(bytes_per_step, 1), n_steps)
 
 
 def sgp_spatial_embedding(x, num_nodes, edge_index, edge_weight=None, k=2, undirected=False,

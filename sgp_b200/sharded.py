@@ -425,7 +425,8 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
     del x
     D = enc.output_size
     # >= 32 chunks per pass so that the 3-stage pipeline has something to overlap
-    step = args.chunk or max(1, min((T + 31) // 32, (args.chunk_mb << 20) // max(sh.plan.n_own * D * 4, 1)))
+    from .preprocessing import round_chunk_steps
+    step = args.chunk or round_chunk_steps(min((T + 31) // 32, (args.chunk_mb << 20) // max(sh.plan.n_own * D * 4, 1)), T)
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def one_pass(breakdown=None):

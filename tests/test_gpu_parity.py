@@ -541,7 +541,8 @@ def test_fused_checksum_equals_sum_of_output():
         assert abs(float(acc) - float(total)) <= 1e-9 * 13 * N * enc.output_size + 1e-7 * abs(float(total))
         acc2 = torch.zeros(1, dtype=torch.float64, device=DEV)
         enc.encode_stream(x, torch.from_numpy(ei), torch.from_numpy(ew), None, checksum=acc2)   # sink-less run
-        assert abs(float(acc2) - float(acc)) <= 1e-9 * abs(float(acc)) + 1e-9
+        # (run-to-run: the global block's node sums use fp32 atomics, so two runs agree to ~1e-8)
+        assert abs(float(acc2) - float(acc)) <= 1e-7 * abs(float(acc)) + 1e-6
 
 
 def test_spmm_tensor_core_row_offsets_beyond_4gb():
@@ -696,3 +697,112 @@ def test_preprocess_dataset_and_reservoir_preprocessing():
     r = sgp_b200.reservoir_preprocessing_(torch.from_numpy(x), cuda=True, **rk)
     assert r.device.type == "cpu"
     assert_blocks_close(r.numpy(), h, 48)
+
+
+# ---------------------------------------------------------------- the callers either side
+def test_iid_sampler_matches_reference_indexing():
+    """f1: IIDDataset.sample on a device-resident [T, N, D] tensor — same host RNG calls, same
+    indices, bit-exact gathers (lib/datasets/iid_dataset.py:57-99)."""
+    T, N, D, C = 300, 77, 640, 2
+    g = np.random.default_rng(0)
+    x, y = g.standard_normal((T, N, D)).astype(np.float32), g.standard_normal((T, N, C)).astype(np.float32)
+    u = g.standard_normal((T, 4)).astype(np.float32)
+    for horizon, delay, lag in [(12, 0, 1), (6, 2, 2)]:
+        s = sgp_b200.IIDSampler(torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV), horizon, delay, lag,
+                                u=torch.from_numpy(u).to(DEV), batch_size=513, num_batches=3)
+        torch.manual_seed(123)
+        batches = list(s)
+        torch.manual_seed(123)
+        for b in batches:
+            step = torch.randint(0, T - horizon, (513,)).numpy()         # the reference's two draws, in order
+            node = torch.randint(0, N, (513,)).numpy()
+            xs, ys = O.iid_sample(x, y, step, node, horizon, delay, lag)
+            assert b["x"].shape == xs.shape and b["y"].shape == ys.shape
+            np.testing.assert_array_equal(b["x"].cpu().numpy(), xs)
+            np.testing.assert_array_equal(b["y"].cpu().numpy(), ys)
+            np.testing.assert_array_equal(b["node_index"].cpu().numpy(), node[:, None])
+            np.testing.assert_array_equal(b["u"].cpu().numpy(), u[step][:, None])
+    # straight from the encoder's output buffer (a strided feature-block view), device RNG
+    buf = torch.randn(50, 40, 3 * 128, device=DEV)
+    s = sgp_b200.IIDSampler(buf[..., 128:256], buf[..., :2], 3, device_rng=True)
+    b = s.sample(64)
+    t, n = (b["y"].shape, b["node_index"][:, 0])
+    assert b["x"].shape == (64, 1, 1, 128) and t == (64, 3, 1, 2) and int(n.max()) < 40
+
+
+@pytest.mark.parametrize("kw", [dict(k=3), dict(k=2, bidirectional=True, global_attr=True),
+                                dict(k=2, undirected=True, add_self_loops=True, bidirectional=True),
+                                dict(k=1, remove_self_loops=True, global_attr=True)])
+def test_spatial_support_vs_dense_oracle(kw):
+    """f2: sgp_spatial_support / SGPLoader.collate / IIDDataset._populate_input_frame on GPU
+    mini-batches against the dense float64 restatement (quirks included)."""
+    n, F, B = 211, 24, 5
+    ei, ew = random_graph(n, 1500, seed=3)
+    sup = sgp_b200.sgp_spatial_support(torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV), n, **kw)
+    ref = O.spatial_support_dense(ei, ew, n, **kw)
+    assert len(sup) == len(ref)
+    x = np.random.default_rng(1).standard_normal((B, n, F)).astype(np.float32)
+    xd = torch.from_numpy(x).to(DEV)
+    idx = torch.tensor([5, 0, 210, 17, 17, 99])
+    for op, S in zip(sup, ref):
+        assert tuple(op.sparse_sizes()) == (n, n)
+        assert_blocks_close((op @ xd).cpu().numpy(), S @ x.astype(np.float64), F)
+        sub = op.index_select(0, idx)
+        assert_blocks_close((sub @ xd).cpu().numpy(), S[idx.numpy()] @ x.astype(np.float64), F)
+    full = sgp_b200.sgp_collate_features(xd, sup)
+    want = np.concatenate([x] + [S @ x.astype(np.float64) for S in ref], -1)
+    assert full.shape == want.shape
+    assert_blocks_close(full.cpu().numpy(), want, F)
+    part = sgp_b200.sgp_collate_features(xd, sup, node_index=idx)
+    assert_blocks_close(part.cpu().numpy(), want[:, idx.numpy()], F)
+
+
+@pytest.mark.parametrize("G,Cin,Cout,rows", [(5, 256, 51, 4096), (10, 64, 25, 1000), (3, 7, 5, 33), (1, 128, 256, 77)])
+def test_grouped_pointwise_conv_vs_torch_conv1d(G, Cin, Cout, rows):
+    """f3: the first decoder layer (nn.Conv1d(kernel_size=1, groups=order) between two Rearranges,
+    lib/nn/models/sgp_model.py:41-52): same parameters and initialisation as nn.Conv1d, forward
+    against the reference's own op in float64, gradients against autograd through nn.Conv1d."""
+    torch.manual_seed(G * Cin)
+    ref = torch.nn.Conv1d(G * Cin, G * Cout, kernel_size=1, groups=G)
+    torch.manual_seed(G * Cin)
+    mine = sgp_b200.GroupedPointwiseConv(G * Cin, G * Cout, groups=G)
+    assert torch.equal(mine.weight.data, ref.weight.data) and torch.equal(mine.bias.data, ref.bias.data)
+    mine = mine.to(DEV)
+    x = torch.randn(2, rows, G * Cin)
+    xd = x.to(DEV).requires_grad_(True)
+    y = mine(xd)
+    want = O.grouped_conv1x1(x.numpy(), ref.weight.data.numpy(), ref.bias.data.numpy(), G)
+    assert y.shape == want.shape
+    np.testing.assert_allclose(y.detach().cpu().numpy(), want, rtol=2e-5, atol=2e-5)
+    xr = x.clone().requires_grad_(True)
+    ref(xr.permute(0, 2, 1)).permute(0, 2, 1).square().sum().backward()
+    y.square().sum().backward()
+    np.testing.assert_allclose(mine.weight.grad.cpu().numpy(), ref.weight.grad.numpy(), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(mine.bias.grad.cpu().numpy(), ref.bias.grad.numpy(), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), xr.grad.numpy(), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("H,L,act,decay", [(32, 2, "tanh", True), (64, 1, "relu", False), (48, 2, "self_norm", False),
+                                           (128, 1, "tanh", False)])
+def test_dyn_gesn_encoder_vs_oracle(H, L, act, decay):
+    """f4: GESNEncoder (SpMM inside the recurrence) against the float64 restatement; weights drawn
+    twice like GraphESN.__init__, unit self-loops added on top of the stored diagonal."""
+    N, T, Fin = 150, 30, 3
+    ei, ew = sensor_thresh(N, 6 * N, seed=2)
+    ei = np.concatenate([ei, np.array([[3, 9], [3, 9]])], 1)              # two stored self loops
+    ew = np.concatenate([ew, np.array([0.5, 0.25], np.float32)])
+    x = sensor_signal(T, N, seed=6)
+    torch.manual_seed(4)
+    enc = sgp_b200.GESNEncoder(Fin, H, L, 0.8, 0.9, 0.7, 1.0, decay, reservoir_activation=act)
+    torch.manual_seed(4)
+    layers = O.draw_graph_esn(Fin, H, L, 0.8, 0.9, 0.7, 1.0, decay)
+    for cell, ref in zip(enc.reservoir.rnn_cells, layers):
+        assert torch.equal(cell.w_hh.data, ref["w_hh"]) and torch.equal(cell.w_ih.data, ref["w_ih"])
+        assert float(cell.alpha) == float(ref["alpha"])
+    y = enc(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ew))
+    assert y.device.type == "cpu" and y.shape == (T, N, L * H)
+    S = O.gesn_operator_dense(ei, ew, N)
+    want = O.graph_esn_states(x, layers, S, act)
+    assert_blocks_close(y.numpy(), want, H)
+    with pytest.raises(TypeError):
+        enc(torch.from_numpy(x), torch.from_numpy(ei), None)

@@ -240,3 +240,49 @@ def test_operator_all_flags_vs_dense_scipy_and_torch_sparse(flags, weighted):
     for got in (S @ x, (St @ torch.from_numpy(x)).numpy(), O.spmm_loops(rowptr, col, val, x[None])[0],
                 O.spmm(rowptr, col, val, x[None], impl="c")[0]):
         np.testing.assert_allclose(got, y_np, rtol=1e-5, atol=1e-6)
+
+
+# ---- SURVEY.md 8(f) restatements: hand-computed anchors --------------------------------------
+def test_spatial_support_quirks():
+    """[S, S^2, S^2] (never S^3), bidirectional = the row-normalised forward adjacency again, the
+    dense 1/N matrix last (lib/sgp_preprocessing.py:143-158)."""
+    A, ei, ew = path3()
+    sup = O.spatial_support_dense(ei, ew, 3, k=3, bidirectional=True, global_attr=True)
+    assert len(sup) == 7
+    S = sup[0]
+    np.testing.assert_allclose(sup[1], S @ S)
+    np.testing.assert_allclose(sup[2], S @ S)                     # not S^3
+    for a, b in zip(sup[:3], sup[3:6]):
+        np.testing.assert_allclose(a, b)                          # the un-transposed recursion
+    np.testing.assert_allclose(sup[6], np.full((3, 3), 1 / 3))
+    und = O.spatial_support_dense(ei, ew, 3, k=1, undirected=True, bidirectional=True)
+    assert und[0].shape == (3, 3) and not np.allclose(und[0], und[1])   # gcn norm vs row norm of A + A^T
+    np.testing.assert_allclose(und[1], (A + A.T) / (A + A.T).sum(1, keepdims=True))
+    np.testing.assert_allclose(S, A / A.sum(1, keepdims=True))
+
+
+def test_iid_sample_and_grouped_conv_shapes():
+    g = np.random.default_rng(0)
+    x, y = g.standard_normal((20, 5, 6)), g.standard_normal((20, 5, 2))
+    step, node = np.array([0, 3, 16]), np.array([4, 0, 2])
+    xs, ys = O.iid_sample(x, y, step, node, horizon=3)
+    assert xs.shape == (3, 1, 1, 6) and ys.shape == (3, 3, 1, 2)
+    np.testing.assert_array_equal(xs[1, 0, 0], x[3, 0])
+    np.testing.assert_array_equal(ys[2, :, 0], y[17:20, 2])
+    w, b = g.standard_normal((6, 2, 1)), g.standard_normal(6)
+    out = O.grouped_conv1x1(x[:2], w, b, groups=3)
+    want = np.stack([x[:2, :, 2 * gi:2 * gi + 2] @ w[2 * gi:2 * gi + 2, :, 0].T + b[2 * gi:2 * gi + 2]
+                     for gi in range(3)], -2).reshape(2, 5, 6)
+    np.testing.assert_allclose(out, want, rtol=1e-12)
+
+
+def test_gesn_operator_and_step_closed_form():
+    ei = np.array([[0, 1, 1], [1, 0, 1]])                 # 0 -> 1, 1 -> 0, a stored loop on node 1; node 2 isolated
+    S = O.gesn_operator_dense(ei, np.array([2.0, 3.0, 5.0]), 3)
+    # loops appended for nodes 0..1 only (max index + 1); row 1 = {from 0: 2, loop: 5 + 1}; row 2 empty
+    np.testing.assert_allclose(S, [[1 / 4, 3 / 4, 0], [2 / 8, 6 / 8, 0], [0, 0, 0]])
+    layer = dict(w_ih=torch.tensor([[1.0]]), w_hh=torch.tensor([[0.5]]), b_ih=torch.tensor([0.0]), alpha=1.0)
+    x = np.ones((2, 3, 1))
+    out = O.graph_esn_states(x, [layer], S, "identity")
+    np.testing.assert_allclose(out[0, :, 0], [1, 1, 1])
+    np.testing.assert_allclose(out[1, :, 0], 1 + 0.5 * (S @ np.ones(3)))
