@@ -55,12 +55,14 @@ constexpr int kTcABufs = 4;         // A (hi | lo) tiles resident in TMEM
 constexpr int kTcSplitGroups = SGP_TC_SPLIT_GROUPS;   // split groups take items round-robin (group = accumulator index at 4)
 constexpr int kTcSplitWarps = 4 * kTcSplitGroups;   // lo-pass + epilogue warps (warp & 3 = TMEM lane quarter)
 constexpr int kTcIssuers = 2;       // MMA-issuing warps (one elected thread each)
-// -DSGP_TC_REGDRAIN (experimental, NOT validated on hardware yet; default off): the split warps
-// copy their accumulator to registers right after `done`, release it at once and store the rows
-// while they convert the next work item's chunks, so the drain no longer stalls the MMAs.  Needs
-// 24 warps and setmaxnreg: the kernel launches with 80 registers per thread (61 440 of 65 536);
-// the last warpgroup (issuers, slab warp, one idle warp) shrinks to 40, the 16 split warps grow to
-// 96 (49 152 + 10 240 + 5 120 = 64 512); the producers keep their 80 (they need ~72).
+// -DSGP_TC_REGDRAIN (experimental, default off): the split warps copy their accumulator to registers
+// right after `done`, release it at once and store the rows while they convert the next work
+// item's chunks, so the drain no longer stalls the MMAs.  Needs 24 warps and setmaxnreg: the kernel
+// launches with 80 registers per thread (61 440 for the CTA, which is ALL the CTA's pool ever holds:
+// the SM's remaining 4 096 are not allocatable); the last warpgroup (issuers, slab warp, one idle
+// warp) shrinks to 40, the producers keep their 80 (they need ~72), so the 16 split warps can grow
+// to at most (61 440 - 10 240 - 5 120) / 512 = 90 -> 88.  (The first hardware runs asked for 96 and
+// spun forever in USETMAXREG.TRY_ALLOC.)
 #ifdef SGP_TC_REGDRAIN
 constexpr int kTcPadWarps = 2;      // slab warp + one idle warp complete the last warpgroup
 #else
@@ -336,7 +338,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
 #ifdef SGP_TC_REGDRAIN
     } else if (warp < kTcSplitWarps) {
         // ================= split warps, register-drain variant (see kTcPadWarps) ==================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         const int grp = warp >> 2, m = tid & 127;                  // group = accumulator; m = feature = TMEM lane
         const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t d_nb = (uint32_t)d_ns * 4u;                 // row stride in bytes (host checks < 2^32)

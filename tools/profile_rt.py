@@ -16,12 +16,13 @@ x = torch.randn(Tc, N, Fin, device=dev)
 h = torch.zeros(N, H, device=dev)
 buf = torch.empty(Tc, N, 5 * H, device=dev)
 err = torch.zeros(1, dtype=torch.int32, device=dev)
+acc = torch.zeros(1, dtype=torch.float64, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for _ in range(2):
-    ops.reservoir_scan_tc(x, wimg, w_ih, b, 0.9, "tanh", h, buf[..., :H], err)
+    ops.reservoir_scan_tc(x, wimg, w_ih, b, 0.9, "tanh", h, buf[..., :H], err, acc)
 e0.record()
 for _ in range(3):
-    ops.reservoir_scan_tc(x, wimg, w_ih, b, 0.9, "tanh", h, buf[..., :H], err)
+    ops.reservoir_scan_tc(x, wimg, w_ih, b, 0.9, "tanh", h, buf[..., :H], err, acc)
 e1.record(); torch.cuda.synchronize()
 assert int(err.item()) == 0
 print(f"{e0.elapsed_time(e1) / 3 / Tc * 1e3:.1f} us per time step")
