@@ -102,6 +102,20 @@ int sgp_reservoir_scan(const float* x, int64_t x_t_stride, int64_t x_n_stride, i
                        float* out, int64_t out_t_stride, int64_t out_n_stride,
                        int Tc, int N, int H, void* stream);
 
+/* All layers of a SMALL reservoir in one launch (H in {16, 32, 64}, L <= 8, Fin <= 64): the shipped
+ * configurations of the reference (config/traffic/sgp_la.yaml H = 64 x L = 2,
+ * config/largescale_100nn/sgp_pv.yaml H = 16 x L = 8).  Layer l reads layer l-1's new state of the
+ * same step from shared memory (reservoir.py:170-176) and all weights stay resident there.
+ * w_ih / w_hh / bias: HOST arrays of L device pointers ([H, Fin_l] with Fin_0 = Fin, Fin_l = H;
+ * [H, H]; [H], exactly the reference's parameters — no packing); alpha: HOST array [L];
+ * h_state [L, N, H] in/out; out element (t, n, l*H + j).  SGP_EUNSUPPORTED when the shape does not
+ * fit (the caller then runs sgp_reservoir_scan layer by layer). */
+int sgp_reservoir_scan_multi(const float* x, int64_t x_t_stride, int64_t x_n_stride, int Fin,
+                             const float* const* w_ih, const float* const* w_hh, const float* const* bias,
+                             const float* alpha, int act, float* h_state,
+                             float* out, int64_t out_t_stride, int64_t out_n_stride,
+                             int Tc, int N, int H, int L, void* stream);
+
 /* Tensor-core scan (tcgen05, 3xTF32, fp32-accurate): same contract as sgp_reservoir_scan for
  * H in {128, 256}, Fin <= 8, activation tanh / relu / identity.  wimg [H*H*2] = W_hh split into tf32
  * hi / lo images in the kernel's shared-memory layout (sgp_reservoir_tc_pack); w_ih [H, Fin] and bias

@@ -30,6 +30,9 @@ SIGNATURES = {
     "sgp_reservoir_scan": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_float,
                                    c_float, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_int, c_void_p]),
+    "sgp_reservoir_scan_multi": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int,
+                                         c_void_p]),
     "sgp_reservoir_tc_pack": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "sgp_reservoir_scan_tc": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_float,
                                       c_float, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,

@@ -264,6 +264,145 @@ reservoir_scan_tiled(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small reservoirs, ALL layers in one launch (H in {16, 32, 64}: the reference's shipped configs
+// sgp_la.yaml H = 64 x L = 2, sgp_pv.yaml H = 16 x L = 8, the default H = 32).  Per time step the
+// layers run back to back inside the kernel — layer l reads layer l-1's NEW state of the same step
+// (reservoir.py:170-176) from shared memory, never from HBM — and every layer's weights
+// ([W_ih^T ; W_hh^T], k-major) stay resident in shared memory for the whole chunk.
+//   * warp = TN nodes per lane group; a lane group (LPN = min(32, H) lanes) covers one node row,
+//     lane jl owns columns jl, jl + LPN (CPL = H / LPN columns); H = 16 packs two groups per warp;
+//   * per 4 k-rows: 4 CPL weight LDS (conflict-free), then per node one LDS.128 of its input /
+//     state row (broadcast) feeding 4 CPL FFMA;
+//   * the node rows [x_t | h_0 | .. | h_{L-1}] are private to the warp: only __syncwarp per layer.
+// Bound: fp32 FMA issue / step latency; HBM bytes per node-step 4 (Fin + L H).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallMaxLayers = 8;
+struct SmallLayers {
+    const float* w_ih[kSmallMaxLayers];    // [H, Fin_l]
+    const float* w_hh[kSmallMaxLayers];    // [H, H]
+    const float* bias[kSmallMaxLayers];    // [H]
+    float alpha[kSmallMaxLayers];
+};
+
+template <int H, int TN>
+__global__ void __launch_bounds__(256)
+reservoir_scan_small(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int Fin, const SmallLayers lay,
+                     int L, int act, float* __restrict__ h_state, float* __restrict__ out, int64_t o_ts,
+                     int64_t o_ns, int Tc, int N) {
+    constexpr int LPN = H < 32 ? H : 32;           // lanes per node row
+    constexpr int CPL = H / LPN;                    // columns per lane
+    constexpr int GPW = 32 / LPN;                   // node groups per warp
+    constexpr int NPW = TN * GPW;                   // nodes per warp
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int FinP = (Fin + 3) & ~3;
+    const int ROW = FinP + L * H;                   // [x | h_0 | ... | h_{L-1}]
+    // weights: layer l at woff(l): (Kin_l + H) rows of H floats, Kin_0 = FinP, Kin_l = H
+    float* wsm = smem;
+    const int w_total = (FinP + H) * H + (L - 1) * 2 * H * H;
+    float* bsm = wsm + w_total;                     // [L][H]
+    float* rows = bsm + L * H + (size_t)warp * NPW * ROW;
+    for (int l = 0; l < L; ++l) {
+        const int Kin = l == 0 ? Fin : H, KinP = l == 0 ? FinP : H;
+        float* w = wsm + (l == 0 ? 0 : (FinP + H) * H + (l - 1) * 2 * H * H);
+        for (int i = threadIdx.x; i < (KinP + H) * H; i += blockDim.x) {
+            const int k = i / H, j = i % H;
+            float v = 0.f;
+            if (k < KinP) { if (k < Kin) v = __ldg(lay.w_ih[l] + (size_t)j * Kin + k); }
+            else v = __ldg(lay.w_hh[l] + (size_t)j * H + (k - KinP));
+            w[i] = v;
+        }
+        for (int j = threadIdx.x; j < H; j += blockDim.x) bsm[l * H + j] = __ldg(lay.bias[l] + j);
+    }
+    const int grp = lane / LPN, jl = lane % LPN;
+    const int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * NPW;
+    // initial state, zero the x padding
+    for (int i = lane; i < NPW * ROW; i += 32) {
+        const int m = i / ROW, c = i % ROW;
+        const int n = n0 + m;
+        float v = 0.f;
+        if (c >= FinP && n < N) { const int l = (c - FinP) / H; v = h_state[((size_t)l * N + n) * H + (c - FinP) % H]; }
+        rows[i] = v;
+    }
+    __syncthreads();
+    for (int t = 0; t < Tc; ++t) {
+        for (int i = lane; i < NPW * Fin; i += 32) {
+            const int m = i / Fin, f = i % Fin, n = n0 + m;
+            rows[m * ROW + f] = n < N ? __ldg(x + (size_t)t * x_ts + (size_t)n * x_ns + f) : 0.f;
+        }
+        __syncwarp();
+        for (int l = 0; l < L; ++l) {
+            const int KinP = l == 0 ? FinP : H;
+            const float* w = wsm + (l == 0 ? 0 : (FinP + H) * H + (l - 1) * 2 * H * H);
+            const int in_off = l == 0 ? 0 : FinP + (l - 1) * H, st_off = FinP + l * H;
+            float acc[TN][CPL];
+#pragma unroll
+            for (int m = 0; m < TN; ++m)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) acc[m][c] = bsm[l * H + jl + c * LPN];
+            // two row segments: the layer's input (x or the previous layer's new state), then its own state
+#pragma unroll 1
+            for (int seg = 0; seg < 2; ++seg) {
+                const int K = seg == 0 ? KinP : H, a_off = seg == 0 ? in_off : st_off;
+                const float* ws = w + (seg == 0 ? 0 : KinP * H);
+#pragma unroll 2
+                for (int k = 0; k < K; k += 4) {
+                    float wv[4][CPL];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) wv[kk][c] = ws[(k + kk) * H + jl + c * LPN];
+#pragma unroll
+                    for (int m = 0; m < TN; ++m) {
+                        const float4 a = *reinterpret_cast<const float4*>(rows + (grp * TN + m) * ROW + a_off + k);
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) {
+                            acc[m][c] = fmaf(a.x, wv[0][c], acc[m][c]);
+                            acc[m][c] = fmaf(a.y, wv[1][c], acc[m][c]);
+                            acc[m][c] = fmaf(a.z, wv[2][c], acc[m][c]);
+                            acc[m][c] = fmaf(a.w, wv[3][c], acc[m][c]);
+                        }
+                    }
+                }
+            }
+            const float alpha = lay.alpha[l], oma = 1.f - alpha;
+            float scale[TN];
+#pragma unroll
+            for (int m = 0; m < TN; ++m) {
+                scale[m] = 1.f;
+                if (act == SGP_ACT_SELF_NORM) {
+                    float ss = 0.f;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) ss = fmaf(acc[m][c], acc[m][c], ss);
+#pragma unroll
+                    for (int o = LPN / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                    scale[m] = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+                }
+            }
+            __syncwarp();                            // every lane is done reading the old state rows
+#pragma unroll
+            for (int m = 0; m < TN; ++m) {
+                const int n = n0 + grp * TN + m;
+                float* r = rows + (grp * TN + m) * ROW + st_off;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const int j = jl + c * LPN;
+                    const float z = act == SGP_ACT_SELF_NORM ? acc[m][c] * scale[m] : activate(acc[m][c], act);
+                    const float v = fmaf(alpha, z, oma * r[j]);
+                    r[j] = v;
+                    if (n < N) out[(size_t)t * o_ts + (size_t)n * o_ns + l * H + j] = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < NPW * L * H; i += 32) {
+        const int m = i / (L * H), c = i % (L * H), n = n0 + m;
+        if (n < N) h_state[((size_t)(c / H) * N + n) * H + c % H] = rows[m * ROW + FinP + c];
+    }
+}
+
 // Generic kernel: any H, any Fin.  One warp per node, lanes stride over the output columns,
 // W^T read through L1/L2 (coalesced over the column index), A row [x_t | h] in shared memory.
 constexpr int kGenWarps = 8;
@@ -411,4 +550,61 @@ extern "C" int sgp_reservoir_scan(const float* x, int64_t x_t_stride, int64_t x_
         out_t_stride, out_n_stride, Tc, N, H);
     SGP_LAUNCH_CHECK("reservoir_scan_generic");
     return SGP_OK;
+}
+
+template <int H, int TN>
+static int launch_small(const float* x, int64_t x_ts, int64_t x_ns, int Fin, const SmallLayers& lay, int L, int act,
+                        float* h_state, float* out, int64_t o_ts, int64_t o_ns, int Tc, int N, cudaStream_t st) {
+    constexpr int LPN = H < 32 ? H : 32, NPW = TN * (32 / LPN), WARPS = 8;
+    const int FinP = (Fin + 3) & ~3, ROW = FinP + L * H;
+    const size_t smem = ((size_t)(FinP + H) * H + (size_t)(L - 1) * 2 * H * H + (size_t)L * H +
+                         (size_t)WARPS * NPW * ROW) * sizeof(float);
+    if (smem > 200 * 1024) return 1;
+    auto kern = reservoir_scan_small<H, TN>;
+    SGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_cta = WARPS * NPW;
+    kern<<<(N + per_cta - 1) / per_cta, WARPS * 32, smem, st>>>(x, x_ts, x_ns, Fin, lay, L, act, h_state, out,
+                                                                 o_ts, o_ns, Tc, N);
+    SGP_LAUNCH_CHECK("reservoir_scan_small");
+    return SGP_OK;
+}
+
+template <int H>
+static int launch_small_h(const float* x, int64_t x_ts, int64_t x_ns, int Fin, const SmallLayers& lay, int L,
+                          int act, float* h_state, float* out, int64_t o_ts, int64_t o_ns, int Tc, int N,
+                          cudaStream_t st) {
+    // wide node tiles only when there are enough nodes to keep every SM busy with them
+    constexpr int G = 32 / (H < 32 ? H : 32);
+    int rc = 1;
+    if (N >= 8 * 8 * G * kNumSMs) rc = launch_small<H, 8>(x, x_ts, x_ns, Fin, lay, L, act, h_state, out, o_ts, o_ns, Tc, N, st);
+    if (rc == 1 && N >= 8 * 4 * G * kNumSMs) rc = launch_small<H, 4>(x, x_ts, x_ns, Fin, lay, L, act, h_state, out, o_ts, o_ns, Tc, N, st);
+    if (rc == 1) rc = launch_small<H, 2>(x, x_ts, x_ns, Fin, lay, L, act, h_state, out, o_ts, o_ns, Tc, N, st);
+    return rc;
+}
+
+extern "C" int sgp_reservoir_scan_multi(const float* x, int64_t x_t_stride, int64_t x_n_stride, int Fin,
+                                        const float* const* w_ih, const float* const* w_hh,
+                                        const float* const* bias, const float* alpha, int act, float* h_state,
+                                        float* out, int64_t out_t_stride, int64_t out_n_stride, int Tc, int N,
+                                        int H, int L, void* stream) {
+    SGP_REQUIRE(x && w_ih && w_hh && bias && alpha && h_state && out, SGP_EINVAL, "sgp_reservoir_scan_multi: null pointer");
+    SGP_REQUIRE(Fin >= 1 && N >= 0 && Tc >= 0 && L >= 1, SGP_EINVAL, "sgp_reservoir_scan_multi: Fin=%d N=%d Tc=%d L=%d", Fin, N, Tc, L);
+    SGP_REQUIRE(act >= SGP_ACT_TANH && act <= SGP_ACT_IDENTITY, SGP_EINVAL, "sgp_reservoir_scan_multi: activation %d", act);
+    SGP_REQUIRE((H == 16 || H == 32 || H == 64) && L <= kSmallMaxLayers && Fin <= 64, SGP_EUNSUPPORTED,
+                "sgp_reservoir_scan_multi: H=%d L=%d Fin=%d (H in {16,32,64}, L <= %d, Fin <= 64)", H, L, Fin, kSmallMaxLayers);
+    if (N == 0 || Tc == 0) return SGP_OK;
+    SmallLayers lay{};
+    for (int l = 0; l < L; ++l) {
+        SGP_REQUIRE(w_ih[l] && w_hh[l] && bias[l], SGP_EINVAL, "sgp_reservoir_scan_multi: null weights of layer %d", l);
+        lay.w_ih[l] = w_ih[l]; lay.w_hh[l] = w_hh[l]; lay.bias[l] = bias[l]; lay.alpha[l] = alpha[l];
+    }
+    cudaStream_t st = as_stream(stream);
+    int rc;
+#define SGP_SMALL_ARGS x, x_t_stride, x_n_stride, Fin, lay, L, act, h_state, out, out_t_stride, out_n_stride, Tc, N, st
+    if (H == 64) rc = launch_small_h<64>(SGP_SMALL_ARGS);
+    else if (H == 32) rc = launch_small_h<32>(SGP_SMALL_ARGS);
+    else rc = launch_small_h<16>(SGP_SMALL_ARGS);
+#undef SGP_SMALL_ARGS
+    SGP_REQUIRE(rc != 1, SGP_EUNSUPPORTED, "sgp_reservoir_scan_multi: H=%d x L=%d does not fit shared memory", H, L);
+    return rc;
 }

@@ -55,19 +55,7 @@ constexpr int kTcABufs = 4;         // A (hi | lo) tiles resident in TMEM
 constexpr int kTcSplitGroups = SGP_TC_SPLIT_GROUPS;   // split groups take items round-robin (group = accumulator index at 4)
 constexpr int kTcSplitWarps = 4 * kTcSplitGroups;   // lo-pass + epilogue warps (warp & 3 = TMEM lane quarter)
 constexpr int kTcIssuers = 2;       // MMA-issuing warps (one elected thread each)
-// -DSGP_TC_REGDRAIN (experimental, default off): the split warps copy their accumulator to registers
-// right after `done`, release it at once and store the rows while they convert the next work
-// item's chunks, so the drain no longer stalls the MMAs.  Needs 24 warps and setmaxnreg: the kernel
-// launches with 80 registers per thread (61 440 for the CTA, which is ALL the CTA's pool ever holds:
-// the SM's remaining 4 096 are not allocatable); the last warpgroup (issuers, slab warp, one idle
-// warp) shrinks to 40, the producers keep their 80 (they need ~72), so the 16 split warps can grow
-// to at most (61 440 - 10 240 - 5 120) / 512 = 90 -> 88.  (The first hardware runs asked for 96 and
-// spun forever in USETMAXREG.TRY_ALLOC.)
-#ifdef SGP_TC_REGDRAIN
-constexpr int kTcPadWarps = 2;      // slab warp + one idle warp complete the last warpgroup
-#else
 constexpr int kTcPadWarps = 1;      // the slab warp
-#endif
 constexpr int kTcStages = 8;        // gathered-row ring in shared memory
 constexpr int kTcStageBytes = kTcKC * 128 * 4;      // 16 KB: 32 rows x 128 features, row-major
 constexpr int kTcBBytes = 2 * kTcR * kTcKC * 4;     // 16 KB: hi + lo image of one chunk
@@ -198,11 +186,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         for (int b = 0; b < kTcABufs; ++b) {
             mbar_init(&ready[b], 4);
             mbar_init(&afree[b], 1);
-#ifdef SGP_TC_REGDRAIN
-            mbar_init(&accfree[b], 4);                  // the accumulator's own split group reads all of it
-#else
             mbar_init(&accfree[b], kTcSplitWarps);      // every split warp drains a slice of every accumulator
-#endif
         }
         for (int b = 0; b < kTcBBufs; ++b) {
             mbar_init(&bfree[b], kTcIssuers);
@@ -245,18 +229,6 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
         return w_ < n_work;
     };
 
-#ifdef SGP_TC_REGDRAIN
-    // Register re-partitioning, ONE instruction per warpgroup and before the roles diverge:
-    // setmaxnreg is .sync.aligned over the 4 warps of a warpgroup, and the last warpgroup's warps
-    // (2 issuers, slab warp, idle warp) take three different role branches below — executing the
-    // (textually identical) instruction in each branch is a different instruction per warp and
-    // hung the first hardware run.
-    // (the dec sits at the top of the branch the WHOLE last warpgroup takes, the inc at the top of the
-    // split branch: ptxas allocates each region with the count set at its head)
-#define SGP_TC_LAST_GROUP_REGS() asm volatile("setmaxnreg.dec.sync.aligned.u32 40;")
-#else
-#define SGP_TC_LAST_GROUP_REGS() do { } while (0)
-#endif
     // The CTA is persistent.  All barrier phases run on counters that continue across work
     // items: `it` items, `cc` chunks, (bi, bph) slab buffers, `wn` work items with at least one
     // chunk.  The producers simply run on into the next work item while the split warps drain the
@@ -335,138 +307,6 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-#ifdef SGP_TC_REGDRAIN
-    } else if (warp < kTcSplitWarps) {
-        // ================= split warps, register-drain variant (see kTcPadWarps) ==================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-        const int grp = warp >> 2, m = tid & 127;                  // group = accumulator; m = feature = TMEM lane
-        const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t d_nb = (uint32_t)d_ns * 4u;                 // row stride in bytes (host checks < 2^32)
-        int it0 = 0, cc = 0, wn = 0;
-        bool ok = true;
-        double csum = 0.0;          // fused sink: sum of every value this thread stores
-        // rows [16, 64) of the previous work item's accumulator, waiting to be stored
-        uint32_t pa[16], pb[16], pc[16];     // three separate arrays: they must stay in registers
-        int pending = 0, p_row0 = -1, p_row1 = -1;
-        const char* p_dp = nullptr;
-        auto store16 = [&](const uint32_t (&v)[16], int j0, int r0, int r1, const char* dp) {
-            int rows[16];
-#pragma unroll
-            for (int e2 = 0; e2 < 16; ++e2)
-                rows[e2] = __shfl_sync(0xffffffffu, (j0 < 32) ? r0 : r1, (j0 & 31) + e2);
-            float part = 0.f;
-#pragma unroll
-            for (int e2 = 0; e2 < 16; ++e2)
-                if (dp != nullptr && rows[e2] >= 0) {
-                    asm volatile("st.global.cs.b32 [%0], %1;" :: "l"(dp + (uint64_t)(uint32_t)rows[e2] * d_nb), "r"(v[e2]) : "memory");
-                    part += __uint_as_float(v[e2]);
-                }
-            csum += (double)part;
-        };
-        // store 16 of the pending rows (register indices must be compile-time constants)
-        auto service = [&]() {
-            if (pending == 48) store16(pa, 16, p_row0, p_row1, p_dp);
-            else if (pending == 32) store16(pb, 32, p_row0, p_row1, p_dp);
-            else if (pending == 16) store16(pc, 48, p_row0, p_row1, p_dp);
-            if (pending > 0) pending -= 16;
-        };
-        auto convert_item = [&]() -> bool {
-            const int a = grp;
-            const int it = it0 + a, s = it & (kTcStages - 1);
-            if (!warp_wait(&full[s], (it >> 3) & 1, &abort_s, err, lane)) return false;
-            if (cc > 0 && !warp_wait(&afree[a], (cc - 1) & 1, &abort_s, err, lane)) return false;
-            const uint32_t rs = smem_base + s * kTcStageBytes + m * 4;     // row-major stage: [k][feature]
-            const uint32_t ta = lane_addr + kTcAOff + a * 64;
-#pragma unroll
-            for (int k0 = 0; k0 < kTcKC; k0 += 8) {        // quarters: 16 live registers next to the 48 held ones
-                uint32_t hv[8], lv[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float x;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(rs + (k0 + k) * 512));
-                    hv[k] = __float_as_uint(x);
-                    lv[k] = __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
-                }
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                             :: "r"(ta + k0), "r"(hv[0]), "r"(hv[1]), "r"(hv[2]), "r"(hv[3]), "r"(hv[4]), "r"(hv[5]),
-                                "r"(hv[6]), "r"(hv[7]) : "memory");
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                             :: "r"(ta + 32 + k0), "r"(lv[0]), "r"(lv[1]), "r"(lv[2]), "r"(lv[3]), "r"(lv[4]), "r"(lv[5]),
-                                "r"(lv[6]), "r"(lv[7]) : "memory");
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&ready[a]);
-                mbar_arrive(&empty[s]);
-            }
-            ++cc;
-            it0 += kTcAcc;
-            service();              // a quarter of the previous work item's stores rides on every conversion
-            return true;
-        };
-        bool primed = false;
-        for (int ws = 0; ok; ++ws) {
-            int g, t_begin;
-            if (!work_item(ws, g, t_begin)) break;
-            const int n_chunks = chunk_ptr[g + 1] - chunk_ptr[g];
-            const int my_row0 = __ldg(grp_rows + (size_t)g * kTcR + lane);
-            const int my_row1 = __ldg(grp_rows + (size_t)g * kTcR + 32 + lane);
-#pragma unroll 1
-            for (int c = primed ? 1 : 0; c < n_chunks && ok; ++c) ok = convert_item();
-            primed = false;
-            if (!ok) break;
-            {
-                int g2, tb2;
-                if (work_item(ws + 1, g2, tb2) && chunk_ptr[g2 + 1] > chunk_ptr[g2]) {
-                    ok = convert_item();
-                    primed = true;
-                    if (!ok) break;
-                }
-            }
-            while (pending > 0) service();       // a short work item: the held rows must leave before pv is reused
-            if (n_chunks > 0) {
-                if (!warp_wait(&done, wn & 1, &abort_s, err, lane)) { ok = false; break; }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            const int a = grp, t = t_begin + a / NFC;
-            const char* dp = t < Tc ? reinterpret_cast<const char*>(dst + (size_t)t * d_ts + (a % NFC) * 128 + (warp & 3) * 32 + lane) : nullptr;
-            uint32_t v0[16];
-            if (n_chunks > 0) {
-#define SGP_TC_LD16(addr, v)                                                                                     \
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                             \
-                             "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                      \
-                             : "=r"((v)[0]), "=r"((v)[1]), "=r"((v)[2]), "=r"((v)[3]), "=r"((v)[4]), "=r"((v)[5]),   \
-                               "=r"((v)[6]), "=r"((v)[7]), "=r"((v)[8]), "=r"((v)[9]), "=r"((v)[10]), "=r"((v)[11]), \
-                               "=r"((v)[12]), "=r"((v)[13]), "=r"((v)[14]), "=r"((v)[15]) : "r"(addr))
-                SGP_TC_LD16(lane_addr + a * kTcR, v0);
-                SGP_TC_LD16(lane_addr + a * kTcR + 16, pa);
-                SGP_TC_LD16(lane_addr + a * kTcR + 32, pb);
-                SGP_TC_LD16(lane_addr + a * kTcR + 48, pc);
-#undef SGP_TC_LD16
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // the whole accumulator is in registers: the next work item may overwrite it
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&accfree[a]);
-                ++wn;
-            } else {
-#pragma unroll
-                for (int e2 = 0; e2 < 16; ++e2) v0[e2] = 0u;             // group without entries: zero rows
-#pragma unroll
-                for (int e2 = 0; e2 < 16; ++e2) { pa[e2] = 0u; pb[e2] = 0u; pc[e2] = 0u; }
-            }
-            store16(v0, 0, my_row0, my_row1, dp);
-            pending = 48; p_row0 = my_row0; p_row1 = my_row1; p_dp = dp;
-        }
-        while (ok && pending > 0) service();
-        if (chk != nullptr && ok) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-            if (lane == 0) atomicAdd(chk, csum);
-        }
-#else
     } else if (warp < kTcSplitWarps) {
         // ================= split warps: stage (smem) -> A hi | lo tiles (TMEM); epilogue =======
         // four groups of 4 warps; group G takes the items of accumulator a = G (warp & 3 = TMEM lane quarter)
@@ -590,9 +430,7 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
             for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
             if (lane == 0) atomicAdd(chk, csum);
         }
-#endif
     } else {
-      SGP_TC_LAST_GROUP_REGS();         // issuers, slab warp (and the idle warp): one warpgroup, one branch
       if (warp == kTcSplitWarps + kTcProducerWarps + kTcIssuers) {
         // ================= slab warp: fp32 slab image -> tf32 hi | lo images ======================
         // The operator stores each chunk's [64 rows x 32 columns] slab once, as fp32 in the K-major
@@ -633,8 +471,6 @@ spmm_rbu_tc_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __restr
                 if (++bi == kTcBBufs) { bi = 0; ++bph; }
             }
         }
-      } else if (warp >= kTcSplitWarps + kTcProducerWarps + kTcIssuers + 1) {
-        // idle warp (register-drain builds only): completes the warpgroup for setmaxnreg
       } else {
         // ================= MMA issuers: two warps, ONE elected thread each runs the whole loop ===
         // issuer q takes the items with (a & 1) == q: a lone thread needs ~500 cycles of

@@ -111,6 +111,25 @@ def reservoir_scan(x: torch.Tensor, wpack: torch.Tensor, bias: torch.Tensor, alp
                                     _stream(x.device))
 
 
+def reservoir_scan_multi(x: torch.Tensor, w_ih: list, w_hh: list, bias: list, alphas: list, activation: str,
+                         h_state: torch.Tensor, out: torch.Tensor) -> None:
+    """All layers of a small reservoir (H in {16, 32, 64}) over a chunk in ONE launch: x [Tc,N,Fin],
+    per-layer device weights as the reference holds them (w_ih[l] [H,Fin_l], w_hh[l] [H,H], bias[l]
+    [H]), h_state [L,N,H] in/out, out [Tc,N,>=L*H] view."""
+    _require_cuda(x, h_state, out, *w_ih, *w_hh, *bias)
+    _check_view3(x, "x")
+    _check_view3(out, "out")
+    Tc, N, Fin = x.shape
+    L, H = len(w_hh), int(w_hh[0].shape[0])
+    assert h_state.shape == (L, N, H) and h_state.is_contiguous() and out.shape[:2] == (Tc, N) and out.shape[2] >= L * H
+    assert all(t.is_contiguous() and t.dtype == torch.float32 for t in (*w_ih, *w_hh, *bias))
+    ptrs = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])      # noqa: E731
+    al = (ctypes.c_float * L)(*[float(a) for a in alphas])
+    _call(x.device, "sgp_reservoir_scan_multi", _p(x), x.stride(0), x.stride(1), Fin, ptrs(w_ih), ptrs(w_hh),
+          ptrs(bias), al, ACT_CODES[activation], _p(h_state), _p(out), out.stride(0), out.stride(1), Tc, N, H, L,
+          _stream(x.device))
+
+
 def reservoir_tc_pack(w_hh: torch.Tensor) -> torch.Tensor:
     """W_hh [H, H] -> tf32 hi / lo images for the tensor-core scan (H in {128, 256})."""
     _require_cuda(w_hh)

@@ -144,12 +144,20 @@ class Reservoir(nn.Module):
             layer.reset_parameters()
 
     # ---- device-side execution ------------------------------------------------------------
-    # tensor-core scan: "auto" (node count >= 2048 and the layer qualifies) | "tc" | "cuda"
+    # tensor-core scan: "auto" (node count >= 2048 and the layer qualifies) | "tc" | "cuda" |
+    # "layerwise" (as "cuda", and small reservoirs also run one launch per layer)
     tc_mode = os.environ.get("SGP_B200_RESERVOIR", "auto")
 
     def device_plan(self, device, num_nodes: Optional[int] = None) -> List[tuple]:
         """Per layer ("cuda", wpack, bias, alpha) or ("tc", wimg, w_ih, bias, alpha, err_flag),
         uploaded/packed for `device`."""
+        if self.multi_layer_ok(device):
+            ws = [(l.w_ih.detach().to(device=device, dtype=torch.float32).contiguous(),
+                   l.w_hh.detach().to(device=device, dtype=torch.float32).contiguous(),
+                   (l.b_ih.detach().to(device=device, dtype=torch.float32).contiguous() if l.b_ih is not None
+                    else torch.zeros(self.hidden_size, device=device))) for l in self.reservoir_layers]
+            return [("multi", [w[0] for w in ws], [w[1] for w in ws], [w[2] for w in ws],
+                     [float(l.alpha) for l in self.reservoir_layers])]
         plan = []
         for layer in self.reservoir_layers:
             use_tc = layer.tensor_core_ok() and (
@@ -161,6 +169,16 @@ class Reservoir(nn.Module):
                 plan.append(("cuda", *layer.device_weights(device), float(layer.alpha)))
         return plan
 
+    def multi_layer_ok(self, device=None) -> bool:
+        """Small reservoirs (H in {16, 32, 64}) run all their layers in one launch with the weights
+        resident in shared memory (sgp_reservoir_scan_multi) when they fit (200 KB)."""
+        H, L, Fin = self.hidden_size, self.num_layers, self.input_size
+        if self.tc_mode == "layerwise" or H not in (16, 32, 64) or L > 8 or Fin > 64:
+            return False
+        finp = (Fin + 3) & ~3
+        floats = (finp + H) * H + (L - 1) * 2 * H * H + L * H + 8 * 2 * (32 // min(32, H)) * (finp + L * H)
+        return floats * 4 <= 200 * 1024
+
     def scan_chunk(self, plan, x_chunk: torch.Tensor, h_state: torch.Tensor, out: torch.Tensor,
                    checksum: Optional[torch.Tensor] = None) -> None:
         """Advance all layers over one chunk.  x_chunk [Tc,N,Fin] (device), h_state [L,N,H] in/out,
@@ -169,6 +187,12 @@ class Reservoir(nn.Module):
         fused into the tensor-core scan's epilogue, a separate reduction for the CUDA-core scan)."""
         H = self.hidden_size
         inp = x_chunk
+        if plan and plan[0][0] == "multi":
+            _, w_ih, w_hh, bias, alphas = plan[0]
+            ops.reservoir_scan_multi(x_chunk, w_ih, w_hh, bias, alphas, self.mode, h_state, out)
+            if checksum is not None:
+                ops.checksum_view(out[..., :len(w_hh) * H], checksum)
+            return
         for l, entry in enumerate(plan):
             blk = out[..., l * H:(l + 1) * H]
             if entry[0] == "tc":

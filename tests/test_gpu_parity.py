@@ -806,3 +806,34 @@ def test_dyn_gesn_encoder_vs_oracle(H, L, act, decay):
     assert_blocks_close(y.numpy(), want, H)
     with pytest.raises(TypeError):
         enc(torch.from_numpy(x), torch.from_numpy(ei), None)
+
+
+@pytest.mark.parametrize("H,L,Fin,N,act", [(64, 2, 3, 207, "tanh"), (16, 8, 3, 5016, "tanh"), (32, 3, 1, 70, "relu"),
+                                           (64, 3, 5, 1300, "self_norm"), (16, 1, 2, 9, "tanh"), (32, 1, 3, 20000, "tanh")])
+def test_scan_multi_layer_small_reservoirs(H, L, Fin, N, act):
+    """All layers of a small reservoir in ONE launch (sgp_reservoir_scan_multi: the reference's shipped
+    H = 64 x L = 2 and H = 16 x L = 8 configurations) against the float64 oracle and against the
+    layer-by-layer kernels; state carried across chunks."""
+    torch.manual_seed(H * L + N)
+    layers = O.draw_reservoir(Fin, H, L, 0.9, 0.9, 0.7, 1.0, alpha_decay=(L > 1))
+    T = 23
+    x = np.random.default_rng(N).standard_normal((T, N, Fin)).astype(np.float32)
+    ref = O.reservoir_states(x, layers, act, dtype=torch.float64).numpy()
+    xd = torch.from_numpy(x).to(DEV)
+    w_ih = [l["w_ih"].to(DEV).contiguous() for l in layers]
+    w_hh = [l["w_hh"].to(DEV).contiguous() for l in layers]
+    b = [l["b_ih"].to(DEV).contiguous() for l in layers]
+    al = [float(l["alpha"]) for l in layers]
+    buf = torch.zeros(T, N, L * H + 8, device=DEV)                    # a wider buffer: strided output rows
+    state = torch.zeros(L, N, H, device=DEV)
+    for t0 in range(0, T, 9):
+        ops.reservoir_scan_multi(xd[t0:t0 + 9], w_ih, w_hh, b, al, act, state, buf[t0:t0 + 9])
+    y = buf[..., :L * H].cpu().numpy()
+    assert_blocks_close(y, ref, H)
+    assert float(buf[..., L * H:].abs().max()) == 0.0
+    np.testing.assert_array_equal(state.cpu().numpy(), np.moveaxis(y[-1].reshape(N, L, H), 1, 0))
+    y2, _ = run_scan(x, layers, act)
+    np.testing.assert_allclose(y, y2, rtol=2e-5, atol=2e-6)
+    # and the Reservoir module picks it by itself
+    res = sgp_b200.Reservoir(Fin, H, num_layers=L, activation=act)
+    assert res.device_plan(torch.device(DEV), N)[0][0] == "multi"
