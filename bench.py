@@ -102,10 +102,10 @@ def make_inputs(cfg, T=None, shard=None):
 def make_encoder(cfg):
     import sgp_b200
     torch.manual_seed(2)
-    return sgp_b200.SGPEncoder(input_size=cfg["Fin"], reservoir_size=cfg["H"], reservoir_layers=1,
-                               leaking_rate=0.9, spectral_radius=0.9, density=0.7, input_scaling=1.0,
-                               receptive_field=cfg["K"], bidirectional=False, alpha_decay=False,
-                               global_attr=False)
+    return sgp_b200.SGPEncoder(input_size=cfg["Fin"], reservoir_size=cfg["H"], reservoir_layers=cfg.get("L", 1),
+                               leaking_rate=cfg.get("leak", 0.9), spectral_radius=cfg.get("rho", 0.9), density=0.7,
+                               input_scaling=1.0, receptive_field=cfg["K"], bidirectional=cfg.get("bidir", False),
+                               alpha_decay=cfg.get("decay", False), global_attr=cfg.get("glob", False))
 
 
 # --------------------------------------------------------------------------------------------
@@ -113,25 +113,36 @@ def make_encoder(cfg):
 # torch_sparse, and torch_sparse is not installable here) on the host cores.
 # --------------------------------------------------------------------------------------------
 def cpu_graph_once(cfg, ei, ew):
-    """One-off per graph: edge list -> normalised CSR (the reference's preprocess_adj)."""
+    """One-off per graph: edge list -> normalised CSR (the reference's preprocess_adj), and the
+    reversed graph's for a bidirectional encoder."""
     from oracle import sgp_oracle as O
     t0 = time.perf_counter()
-    op = O.build_operator(ei, ew, cfg["N"], set_diag=False)
-    return op, time.perf_counter() - t0
+    fwd = O.build_operator(ei, ew, cfg["N"], set_diag=False)
+    bwd = O.build_operator(ei[[1, 0]], ew, cfg["N"], set_diag=False) if cfg.get("bidir") else None
+    return (fwd, bwd), time.perf_counter() - t0
 
 
 def cpu_encode_once(cfg, op, x, layers):
-    """Reservoir + K hops over the sample's time steps with a prebuilt operator."""
+    """Reservoir + K hops (+ reversed-graph hops, + global block) over the sample's time steps with
+    prebuilt operators, written block by block into one [Ts, N, D] buffer."""
     from oracle import sgp_oracle as O
-    rowptr, col, val = op
+    fwd, bwd = op
+    K = cfg["K"]
     t0 = time.perf_counter()
     h = O.reservoir_states(x, layers, "tanh")
     t1 = time.perf_counter()
     F = h.shape[-1]
-    out = torch.empty(h.shape[0], cfg["N"], (cfg["K"] + 1) * F)
+    nb = 1 + K * (2 if bwd is not None else 1) + (1 if cfg.get("glob") else 0)
+    out = torch.empty(h.shape[0], cfg["N"], nb * F)
     out[..., :F] = h
-    for k in range(cfg["K"]):
-        O.spmm_c(rowptr, col, val, out[..., k * F:(k + 1) * F], out=out[..., (k + 1) * F:(k + 2) * F])
+    for k in range(K):
+        O.spmm_c(*fwd, out[..., k * F:(k + 1) * F], out=out[..., (k + 1) * F:(k + 2) * F])
+    if bwd is not None:
+        for k in range(K):
+            src = out[..., :F] if k == 0 else out[..., (K + k) * F:(K + k + 1) * F]
+            O.spmm_c(*bwd, src, out=out[..., (K + k + 1) * F:(K + k + 2) * F])
+    if cfg.get("glob"):
+        out[..., (nb - 1) * F:] = out[..., :F].mean(1, keepdim=True)
     t2 = time.perf_counter()
     return dict(reservoir=t1 - t0, spmm=t2 - t1, checksum=float(out[-1].double().sum()))
 
@@ -139,9 +150,10 @@ def cpu_encode_once(cfg, op, x, layers):
 def cpu_sample_steps(cfg):
     """Time steps of the CPU sample: about 4 s of CPU work per step of the run (measured on the
     16-core box: ~3.7e-6 s per node-step at C4), capped by 8 GB of host output."""
-    deg = cfg.get("k", 8)
-    per_step = cfg["N"] * (2 * cfg["H"] * cfg["H"] / 250e9 + 2 * cfg["K"] * deg * cfg["H"] / 70e9) + 2e-4
-    mem_cap = int(8e9 // (cfg["N"] * (cfg["K"] + 1) * cfg["H"] * 4))
+    deg, L = cfg.get("k", 8), cfg.get("L", 1)
+    hops = cfg["K"] * (2 if cfg.get("bidir") else 1)
+    per_step = cfg["N"] * L * (2 * cfg["H"] * cfg["H"] / 250e9 + 2 * hops * deg * cfg["H"] / 70e9) + 2e-4 * L
+    mem_cap = int(8e9 // (cfg["N"] * (hops + 2) * L * cfg["H"] * 4))
     return int(max(2, min(cfg["T"], mem_cap, 4.0 / per_step)))
 
 
@@ -195,8 +207,9 @@ def config_dict(cfg, n_gpus, extra=None):
     adds only cpu_sample_steps); implementation details of the GPU arm go to `kernel_config`."""
     d = dict(workload=f"{cfg['name']}: synthetic sensor graph N={cfg['N']}, "
                       f"{'k=%d-NN' % cfg['k'] if cfg['graph'] == 'knn' else 'thresholded kernel'}, "
-                      f"T={cfg['T']}, H={cfg['H']}, K={cfg['K']}, Fin={cfg['Fin']}, L=1, directed D^-1 A",
-             N=cfg["N"], T=cfg["T"], H=cfg["H"], K=cfg["K"], Fin=cfg["Fin"],
+                      f"T={cfg['T']}, H={cfg['H']}, K={cfg['K']}, Fin={cfg['Fin']}, L={cfg.get('L', 1)}, directed D^-1 A"
+                      f"{', bidirectional' if cfg.get('bidir') else ''}{', global_attr' if cfg.get('glob') else ''}",
+             N=cfg["N"], T=cfg["T"], H=cfg["H"], K=cfg["K"], Fin=cfg["Fin"], L=cfg.get("L", 1),
              l2_policy="inputs larger than L2 (each step streams the whole series; no flush needed)",
              parallelism=f"rows{n_gpus}" if n_gpus > 1 else "single")
     if extra:
@@ -260,10 +273,10 @@ def run_own(args, cfg):
         from sgp_b200 import sharded
         return sharded.bench(args, cfg, rank, world, dev, peaks, config_dict, METRIC, UNIT, clock_sampler=ClockSampler)
 
-    N, T, H, K, Fin = cfg["N"], cfg["T"], cfg["H"], cfg["K"], cfg["Fin"]
-    F, D = H, (K + 1) * H
+    N, T, H, K, Fin, L = cfg["N"], cfg["T"], cfg["H"], cfg["K"], cfg["Fin"], cfg.get("L", 1)
     ei, ew, x = make_inputs(cfg)
     enc = make_encoder(cfg)
+    F, D = L * H, enc.output_size
     from sgp_b200.preprocessing import round_chunk_steps
     enc.chunk_steps = args.chunk or round_chunk_steps((args.chunk_mb << 20) // (N * D * 4), T)
     step_T = enc.chunk_steps
@@ -280,7 +293,10 @@ def run_own(args, cfg):
     plan = enc.reservoir.device_plan(dev, N)
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     bufs = [torch.empty(step_T, N, D, device=dev) for _ in range(2)]
-    state = torch.zeros(1, N, H, device=dev)
+    state = torch.zeros(L, N, H, device=dev)
+    sums = torch.empty(step_T, F, device=dev) if cfg.get("glob") else None
+    from sgp_b200.preprocessing import spatial_blocks
+    hop_list = [(fwd, 0)] + ([(bwd, K)] if bwd is not None else [])
 
     def one_pass(timed=None):
         # the sink is the checksum `acc`: accumulated by the producing kernels in their epilogues
@@ -290,13 +306,19 @@ def run_own(args, cfg):
             buf = bufs[i % 2][: t1 - t0]
             if timed is None:
                 enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf, acc)
-                enc.sgp_encoder.encode_chunk(buf, F, fwd, bwd, checksum=acc)
+                enc.sgp_encoder.encode_chunk(buf, F, fwd, bwd, sums, checksum=acc)
             else:
                 timed.wrap("scan", lambda: enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf, acc))
-                for h in range(1, K + 1):
-                    timed.wrap(("spmm", t1 - t0), lambda h=h: fwd.apply(buf[..., (h - 1) * F:h * F],
-                                                                        buf[..., h * F:(h + 1) * F],
-                                                                        checksum=acc))
+                for op, base in hop_list:
+                    for h in range(1, K + 1):
+                        src = buf[..., :F] if h == 1 else buf[..., (base + h - 1) * F:(base + h) * F]
+                        timed.wrap(("spmm", t1 - t0), lambda op=op, src=src, h=h, base=base: op.apply(
+                            src, buf[..., (base + h) * F:(base + h + 1) * F], checksum=acc))
+                if cfg.get("glob"):
+                    g = spatial_blocks(K, bwd is not None)
+                    ops.node_sum(buf[..., :F], sums[: t1 - t0])
+                    ops.node_mean_broadcast(sums[: t1 - t0], N, buf[..., g * F:(g + 1) * F])
+                    ops.checksum_view(buf[..., g * F:(g + 1) * F], acc)
 
     for _ in range(args.warmup):
         one_pass()
@@ -332,7 +354,7 @@ def run_own(args, cfg):
     avg_ms = ms_full / max(n_full, 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
     scan_n, scan_ms = summ.get("scan", (0, 0.0))
-    scan_flops = N * T * (2 * H * (Fin + H) + 6 * H) * args.steps
+    scan_flops = N * T * ((2 * H * (Fin + H) + 6 * H) + (L - 1) * (4 * H * H + 6 * H)) * args.steps
     fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     hop_kernel = ("spmm_rbu_tc_kernel" if fwd.tc is not None else
                   ("spmm_rbu_v3<%d>" % fwd.rbu.R) if fwd.rbu is not None else "spmm_csr_vec")
@@ -349,7 +371,8 @@ def run_own(args, cfg):
                     gflops=flops_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0,
                     fp32_fma_peak_tflops=fma_peak,
                     share_of_step=spmm_ms / (args.steps * ms_step) if ms_step else None)
-    reservoir = dict(kernel="reservoir_tc_kernel (tcgen05, 3xTF32)" if plan[0][0] == "tc" else "reservoir_scan_tiled", ms_per_step=scan_ms / args.steps,
+    reservoir = dict(kernel={"tc": "reservoir_tc_kernel (tcgen05, 3xTF32)", "multi": "reservoir_scan_small (all layers, one launch)",
+                             "cuda": "reservoir_scan_tiled / generic"}[plan[0][0]], ms_per_step=scan_ms / args.steps,
                      tflops=scan_flops / (scan_ms * 1e-3) / 1e12 if scan_ms else 0.0,
                      frac_of_fp32_fma_peak=(scan_flops / (scan_ms * 1e-3) / 1e12) / fma_peak if scan_ms else 0.0,
                      share_of_step=scan_ms / (args.steps * ms_step) if ms_step else None)

@@ -95,6 +95,12 @@ CONFIGS = {
     "c3_pv_us": dict(N=5016, graph="knn", k=100, T=10000, H=256, K=4, Fin=3),
     "c4_100k": dict(N=100_000, graph="knn", k=100, T=1000, H=256, K=4, Fin=1),
     "c5_1m": dict(N=1_000_000, graph="knn", k=32, T=256, H=128, K=2, Fin=1),
+    # the reference's SHIPPED encoder configurations at their datasets' shapes (sgp_paper.pdf Table 3):
+    # config/traffic/sgp_la.yaml (METR-LA 34272 x 207) and config/largescale_100nn/sgp_pv.yaml (PV-US 8868 x 5016)
+    "la_yaml": dict(N=207, graph="thresh", edges=1515, T=34272, H=64, L=2, K=4, Fin=3, bidir=True, glob=True,
+                    decay=True, leak=0.9, rho=0.9),
+    "pv_yaml": dict(N=5016, graph="knn", k=100, T=8868, H=16, L=8, K=2, Fin=3, bidir=False, glob=True,
+                    decay=True, leak=1.0, rho=0.99),
 }
 
 
