@@ -250,6 +250,15 @@ int sgp_checksum(const float* buf, int64_t count, double* acc, void* stream);
 int sgp_checksum_view(const float* src, int64_t src_t_stride, int64_t src_n_stride, int N, int F, int Tc,
                       double* acc, void* stream);
 
+/* Halo push (row-sharded path): dst_addr[k] + t*dst_t_stride receives src[t, index[k], 0:F] for every
+ * t < Tc.  dst_addr [n_index] is a DEVICE array of 64-bit addresses, normally slots of peer GPUs'
+ * halo buffers mapped into this process: the pack and the NVLink transfer are one kernel.
+ * F % 4 == 0, 16-byte aligned rows.  Ordering against the readers is the caller's business
+ * (a cross-rank barrier before and after, sgp_b200/sharded.py). */
+int sgp_push_rows(const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                  const int32_t* index, const int64_t* dst_addr, int n_index,
+                  int64_t dst_t_stride, int F, int Tc, void* stream);
+
 /* IID (t, n) sampler gather: dst[m, 0:F] = src[t_idx[m], n_idx[m], 0:F] for m in [0, M).
  * Replaces `tens[(step_index, None, None, node_index)]` and `tens[(hor_index, node_index[:, None], None)]`
  * of IIDDataset.sample (lib/datasets/iid_dataset.py:57-99) for a device-resident `tens`.  The index

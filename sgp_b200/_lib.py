@@ -63,6 +63,7 @@ SIGNATURES = {
                                         c_int, c_void_p]),
     "sgp_checksum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "sgp_checksum_view": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sgp_push_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "sgp_gather_tn": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
                               c_void_p, c_int64, c_void_p]),
     "sgp_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64, c_int64,

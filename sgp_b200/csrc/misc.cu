@@ -115,6 +115,26 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int64_t s_ts, 
     }
 }
 
+// Halo PUSH over NVLink: row index[k] of `src` goes, for every time step of the chunk, to the address
+// dst_addr[k] + t * d_ts — a slot of ANOTHER rank's halo buffer, mapped into this process (peer
+// memory: torch symmetric memory / cudaIpc).  The pack and the transfer are one kernel: 16-byte
+// stores straight into the peer's HBM, no send buffer, no collective call; the copy engines and
+// NCCL are not involved, and the kernel (no shared memory, 256 threads) co-resides with the
+// persistent hop CTAs, so the exchange of one chunk runs under the SpMM of the other.
+__global__ void push_rows_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
+                                 const int32_t* __restrict__ index, const int64_t* __restrict__ dst_addr,
+                                 int n_index, int64_t d_ts, int F4, int Tc) {
+    const uint32_t per_t = (uint32_t)n_index * (uint32_t)F4;
+    for (int t = blockIdx.y; t < Tc; t += gridDim.y) {
+        const float* sp = src + (size_t)t * s_ts;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_t; i += gridDim.x * blockDim.x) {
+            const uint32_t k = i / (uint32_t)F4, f = i - k * (uint32_t)F4;
+            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(__ldg(dst_addr + k)) + (size_t)t * d_ts);
+            dp[f] = ldg_f4_stream(sp + (size_t)__ldg(index + k) * s_ns + 4 * f);
+        }
+    }
+}
+
 // dst[m, :] = src[t_idx[m], n_idx[m], :] — the IID (t, n) sampler's gather from the device-resident
 // encoder output (lib/datasets/iid_dataset.py:57-99: `tens[(step_index, None, None, node_index)]`).
 // One warp per sample walks the row in 512-byte pieces (16 bytes per lane) when VEC, else scalars.
@@ -198,6 +218,25 @@ extern "C" int sgp_checksum_view(const float* src, int64_t src_t_stride, int64_t
     checksum_view_kernel<<<grid_1d(rows, rpb * 4), 256, 0, as_stream(stream)>>>(src, src_t_stride, src_n_stride,
                                                                               N, F, Tc, acc);
     SGP_LAUNCH_CHECK("checksum_view");
+    return SGP_OK;
+}
+
+extern "C" int sgp_push_rows(const float* src, int64_t src_t_stride, int64_t src_n_stride, const int32_t* index,
+                             const int64_t* dst_addr, int n_index, int64_t dst_t_stride, int F, int Tc,
+                             void* stream) {
+    SGP_REQUIRE(src && ((index && dst_addr) || n_index == 0), SGP_EINVAL, "sgp_push_rows: null pointer");
+    if (Tc <= 0 || n_index <= 0 || F <= 0) return SGP_OK;
+    SGP_REQUIRE(F % 4 == 0 && aligned16(src) && src_t_stride % 4 == 0 && src_n_stride % 4 == 0 && dst_t_stride % 4 == 0,
+                SGP_EALIGN, "sgp_push_rows: F %% 4 == 0 and 16-byte aligned views required");
+    const int64_t per_t = (int64_t)n_index * (F / 4);
+    SGP_REQUIRE(per_t < (1ll << 32), SGP_EUNSUPPORTED, "sgp_push_rows: %d rows x %d features too large", n_index, F);
+    const int gy = Tc < 64 ? Tc : 64;
+    int gx = (int)((per_t + 255) / 256);
+    const int cap = (kNumSMs * 8 + gy - 1) / gy;
+    gx = gx < 1 ? 1 : (gx > cap ? cap : gx);
+    push_rows_kernel<<<dim3(gx, gy), 256, 0, as_stream(stream)>>>(src, src_t_stride, src_n_stride, index, dst_addr,
+                                                                  n_index, dst_t_stride, F / 4, Tc);
+    SGP_LAUNCH_CHECK("push_rows");
     return SGP_OK;
 }
 

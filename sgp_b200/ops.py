@@ -421,6 +421,16 @@ def grouped_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.T
     return out
 
 
+def push_rows(src: torch.Tensor, index: torch.Tensor, dst_addr: torch.Tensor, dst_t_stride: int) -> None:
+    """Rows index[k] of src [Tc, N, F] -> address dst_addr[k] + t*dst_t_stride (floats) for every t:
+    the halo push into peer-mapped buffers (see sgp_push_rows)."""
+    _check_view3(src, "src")
+    Tc, _, F = src.shape
+    assert index.dtype == torch.int32 and dst_addr.dtype == torch.int64 and index.numel() == dst_addr.numel()
+    _call(src.device, "sgp_push_rows", _p(src), src.stride(0), src.stride(1), _p(index), _p(dst_addr),
+          int(index.numel()), int(dst_t_stride), F, Tc, _stream(src.device))
+
+
 def gather_tn(src: torch.Tensor, t_idx: torch.Tensor, n_idx: torch.Tensor, dst: torch.Tensor) -> None:
     """dst[m, :] = src[t_idx[m], n_idx[m], :]; src a [T, N, F] view, indices device int64 [M]."""
     _require_cuda(src, t_idx, n_idx, dst)

@@ -9,9 +9,15 @@ The reference is single-process; this is the B200-side scaling design named by t
   sgp_partition_rows — halo rows per owned row 0.05 / 0.10 / 0.19 at 2 / 4 / 8 ranks on the
   100k-node 100-NN graph) plus the matching rows of every feature block;
 * before each hop the rows of the previous block that other ranks reference ("halo" rows) are
-  packed on the device (sgp_gather_rows, 16 bytes per thread) and exchanged with ONE all-to-all-v
-  over NVLink; the SpMM kernels then read local columns from the rank's own block and halo
-  columns straight from the receive buffer (second source pointer, no concatenation copy);
+  PUSHED by one kernel (sgp_push_rows) straight into the consumers' halo buffers over NVLink:
+  the buffers are torch symmetric memory mapped into every process, the kernel stores 16 bytes
+  per thread to peer addresses, and a device-side barrier on either side orders it against the
+  readers.  No send buffer, no collective kernel: the push (no shared memory) co-resides with the
+  persistent hop CTAs of the other chunk, which an NCCL all-to-all cannot (its CTAs waited for the
+  hop to finish: 32 ms of exposed exchange per pass at 2 GPUs).  ``exchange="nccl"`` keeps the
+  packed all-to-all-v as a fallback where peer mapping is unavailable.  The SpMM kernels read
+  local columns from the rank's own block and halo columns straight from the halo buffer (second
+  source pointer, no concatenation copy);
 * bidirectional / undirected encoders shard the reversed / symmetrised operator by the SAME row
   partition, each with its own halo plan;
 * chunks of time steps flow through a 3-stage pipeline on three CUDA streams: the scan of chunk
@@ -171,13 +177,66 @@ class _NoPhase:
         return None
 
 
+class PeerHalo:
+    """Halo buffers in symmetric memory + per-operator destination address tables for the push."""
+
+    N_LANES = 2
+
+    def __init__(self, operators: List[ShardedOperator], F: int, step: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.F, self.step = F, step
+        # identical size on every rank: the largest halo of any rank / operator
+        n_max = torch.tensor([max(o.plan.n_halo for o in operators)], device=device, dtype=torch.int64)
+        dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=self.group)
+        self.slot = step * F                                   # floats per halo row: [step, F]
+        self.lane_floats = max(int(n_max) * self.slot, 4)
+        self.buf = symm_mem.empty(self.N_LANES * self.lane_floats, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        # every rank's receive layout: recv_counts[p][q] = rows rank p receives from q (its halo is
+        # ordered by source rank), so my rows for p start at slot sum(recv_counts[p][:me])
+        self.addr = []                                          # [operator][lane] -> int64 [n_send] (device)
+        for o in operators:
+            mine = torch.tensor(o.plan.recv_counts, device=device, dtype=torch.int64)
+            allc = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allc, mine, group=self.group)
+            allc = torch.stack(allc).cpu().numpy()              # [p, q]
+            per_lane = []
+            for lane in range(self.N_LANES):
+                parts = []
+                for p in range(world):
+                    n = int(o.plan.send_counts[p])
+                    first = int(allc[p][:rank].sum())
+                    assert n == int(allc[p][rank])
+                    base = ptrs[p] + 4 * lane * self.lane_floats
+                    parts.append(base + 4 * self.slot * (first + np.arange(n, dtype=np.int64)))
+                a = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+                per_lane.append(torch.from_numpy(a).to(device))
+            self.addr.append(per_lane)
+
+    def halo_view(self, lane: int, n_halo: int, Tc: int) -> torch.Tensor:
+        """[Tc, n_halo, F] view of this rank's lane buffer (node-major slots of `step` x F floats)."""
+        flat = self.buf[lane * self.lane_floats: lane * self.lane_floats + max(n_halo, 1) * self.slot]
+        return flat.view(max(n_halo, 1), self.step, self.F)[:n_halo, :Tc].permute(1, 0, 2)
+
+    def barrier(self, lane: int) -> None:
+        # bounded: a peer that never arrives traps the kernel (CUDA error) instead of hanging the box
+        self.hdl.barrier(channel=lane, timeout_ms=20000)
+
+
 class RowShardedEncoder:
     """Runs an :class:`sgp_b200.SGPEncoder` on this rank's rows of the graph."""
 
     N_SLOTS = 3
 
-    def __init__(self, encoder, edge_index, edge_weight, num_nodes: int, device, group=None):
+    def __init__(self, encoder, edge_index, edge_weight, num_nodes: int, device, group=None,
+                 exchange: str = "auto"):
+        """exchange: "p2p" (halo rows pushed into peer-mapped buffers by sgp_push_rows), "nccl"
+        (pack + all_to_all_single), "auto" = p2p when the symmetric-memory rendezvous works."""
         self.enc, self.group, self.dev = encoder, group, torch.device(device)
+        self.exchange_mode, self._peer, self._peer_key = exchange, None, None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         spat = encoder.sgp_encoder
         if spat.undirected:
@@ -218,6 +277,39 @@ class RowShardedEncoder:
     def halo_rows(self) -> int:
         return sum(o.plan.n_halo for o in self.operators)
 
+    def _peer_halo(self, step: int) -> Optional[PeerHalo]:
+        """The symmetric halo buffers for chunks of `step` time steps (built once per step size;
+        collective).  None = use the NCCL exchange."""
+        if self.exchange_mode == "nccl" or self.world == 1:
+            return None
+        if self._peer_key != step:
+            ok = 1
+            try:
+                self._peer = PeerHalo(self.operators, self.F, step, self.dev, self.group)
+            except Exception as e:  # noqa: BLE001 - no peer mapping on this box: fall back together
+                if self.exchange_mode == "p2p":
+                    raise
+                self._peer, self._peer_error, ok = None, repr(e), 0
+            flag = torch.tensor([ok], device=self.dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:
+                self._peer = None
+            self._peer_key = step
+        return self._peer
+
+    def _exchange_p2p(self, peer: PeerHalo, oi: int, sop: ShardedOperator, block: torch.Tensor, lane: int, phase):
+        """barrier (every rank is done reading this lane's halo buffer) -> push my rows into the
+        consumers' buffers -> barrier (every push has landed); returns my halo view."""
+        Tc = block.shape[0]
+        with phase("exchange"):
+            peer.barrier(lane)
+        with phase("pack"):
+            if sop.n_send:
+                ops.push_rows(block, sop.send_index, peer.addr[oi][lane], self.F)
+        with phase("exchange"):
+            peer.barrier(lane)
+        return peer.halo_view(lane, sop.plan.n_halo, Tc)
+
     def _exchange(self, sop: ShardedOperator, block: torch.Tensor, send_flat: torch.Tensor,
                   halo_flat: torch.Tensor, phase):
         """Pack the rows other ranks need from `block` [Tc, n_own, F] and all-to-all them; returns
@@ -255,8 +347,10 @@ class RowShardedEncoder:
         n_send = max(o.n_send for o in self.operators)
         n_halo = max(o.plan.n_halo for o in self.operators)
         bufs = [torch.empty(step, pl.n_own, D, device=dev) for _ in range(self.N_SLOTS)]
-        lanes = [dict(send=torch.empty(max(n_send * step * F, 1), device=dev),
-                      halo=torch.empty(max(n_halo * step * F, 1), device=dev),
+        peer = self._peer_halo(step)
+        self.exchange_used = "p2p push (symmetric memory)" if peer is not None else "nccl all_to_all_v"
+        lanes = [dict(send=None if peer is not None else torch.empty(max(n_send * step * F, 1), device=dev),
+                      halo=None if peer is not None else torch.empty(max(n_halo * step * F, 1), device=dev),
                       sums=torch.empty(step, F, device=dev) if spat.global_attr else None)
                  for _ in range(2)]
         main = torch.cuda.current_stream(dev)
@@ -281,12 +375,15 @@ class RowShardedEncoder:
             hs = self.s_hop[lane]
             with torch.cuda.stream(hs):
                 hs.wait_event(scan_done)
-                for sop, base in ((self.fwd, 0), (self.bwd, K)):
+                for oi, (sop, base) in enumerate(((self.fwd, 0), (self.bwd, K))):
                     if sop is None:
                         continue
                     for h in range(1, K + 1):
                         src = buf[..., :F] if h == 1 else buf[..., (base + h - 1) * F:(base + h) * F]
-                        halo = self._exchange(sop, src, lanes[lane]["send"], lanes[lane]["halo"], phase)
+                        if peer is not None:
+                            halo = self._exchange_p2p(peer, oi, sop, src, lane, phase)
+                        else:
+                            halo = self._exchange(sop, src, lanes[lane]["send"], lanes[lane]["halo"], phase)
                         with phase("hop"):
                             sop.op.apply(src, buf[..., (base + h) * F:(base + h + 1) * F], halo, checksum)
                 if spat.global_attr:
@@ -415,7 +512,8 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
                               bidirectional=False, alpha_decay=False, global_attr=False)
     torch.cuda.synchronize()
     t_b0 = time.perf_counter()
-    sh = RowShardedEncoder(enc, ei_t, ew_t, N, dev)
+    import os
+    sh = RowShardedEncoder(enc, ei_t, ew_t, N, dev, exchange=os.environ.get("SGP_B200_EXCHANGE", "auto"))
     torch.cuda.synchronize()
     build_ms = torch.tensor([(time.perf_counter() - t_b0) * 1e3], device=dev)
     dist.all_reduce(build_ms, op=dist.ReduceOp.MAX)
@@ -497,10 +595,26 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
     dist.all_reduce(halo)
     chk_e2e = torch.tensor([float(chk_host)], device=dev, dtype=torch.float64)
     dist.all_reduce(chk_e2e)
+    # roofline of the hop on the shards: algorithmic bytes of every rank's launches (its rows of the
+    # operator once per launch + its rows of the panel read and written once per time step; halo rows
+    # are traffic, not algorithmic bytes) over the slowest rank's hop time in the instrumented pass
+    n_chunks = (T + step - 1) // step
+    local_bytes = torch.tensor([float(n_chunks * K * (8 * sh.fwd.op.csr.nnz + 4 * (sh.plan.n_own + 1)) +
+                                      K * 2 * T * sh.plan.n_own * H * 4)], device=dev, dtype=torch.float64)
+    dist.all_reduce(local_bytes)
     if rank == 0:
         ms_step = float(ms)
         value = N * T / (ms_step * 1e-3)
         fmt = sh.fwd.op
+        hop_ms = float(bd_max[names.index("hop")])
+        achieved = float(local_bytes) / (hop_ms * 1e-3) / 1e9 if hop_ms else 0.0
+        roofline = dict(bound="hbm", kernel="spmm_rbu_tc_kernel<HALO> on %d shards" % world if fmt.tc is not None else "spmm (CUDA cores)",
+                        achieved=achieved, peak=peaks["hbm_gbs"] * world, unit="GB/s",
+                        frac=achieved / (peaks["hbm_gbs"] * world), peak_source=peaks["source"] + " x n_gpus",
+                        traffic=None, algorithmic_bytes_per_pass_all_ranks=float(local_bytes),
+                        hop_ms_per_pass_slowest_rank=hop_ms,
+                        note="aggregate over ranks: all ranks' algorithmic hop bytes / the slowest rank's hop "
+                             "stream time (instrumented pass, CUDA events)")
         nvlink_bytes = float(halo[0]) * 4 * H * K * T          # halo rows x row bytes x hops x time steps
         line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="strong",
@@ -511,10 +625,10 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
                         operator_format=("tcgen05 64-row groups" if fmt.tc is not None else
                                          "rbu%d" % fmt.rbu.R if fmt.rbu is not None else "csr"),
                         partition="recursive bisection along the patch diameter (sgp_partition_rows)",
-                        exchange="all_to_all_v of halo rows per hop (NCCL); scan / 2 hop chains on 3 streams, "
+                        exchange=sh.exchange_used + " of halo rows per hop; scan / 2 hop chains on 3 streams, "
                                  "3 chunk buffers",
                         sink="fp64 checksum of the whole output, accumulated in the scan / hop epilogues"),
-                    roofline=None,
+                    roofline=roofline,
                     breakdown=dict(
                         unit="ms of stream-busy time per pass, CUDA events on the phase's own stream; phases on "
                              "different streams overlap (sum > ms_per_step); 'exchange' includes waiting for peers",

@@ -43,7 +43,8 @@ for c in CASES:
     err = float((out - ref).abs().max() / ref.abs().max())
     cerr = abs(float(acc) - float(out.double().sum())) / max(abs(float(out.double().sum())), 1.0)
     worst = max(worst, err, cerr)
-    print(f"rank {rank}: {c} own={sh.plan.n_own} halo={sh.halo_rows()} rel err {err:.2e} checksum err {cerr:.1e}", flush=True)
+    print(f"rank {rank}: {c} own={sh.plan.n_own} halo={sh.halo_rows()} exchange={sh.exchange_used!r} "
+          f"{getattr(sh, '_peer_error', '')} rel err {err:.2e} checksum err {cerr:.1e}", flush=True)
 flag = torch.tensor([worst], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MAX)
 if rank == 0:
