@@ -280,7 +280,7 @@ class RowShardedEncoder:
     def _peer_halo(self, step: int) -> Optional[PeerHalo]:
         """The symmetric halo buffers for chunks of `step` time steps (built once per step size;
         collective).  None = use the NCCL exchange."""
-        if self.exchange_mode == "nccl" or self.world == 1:
+        if self.exchange_mode == "nccl" or self.world == 1 or self.F % 16:
             return None
         if self._peer_key != step:
             ok = 1
