@@ -117,28 +117,23 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int64_t s_ts, 
 
 // Halo PUSH over NVLink: row index[k] of `src` goes, for every time step of the chunk, to the address
 // dst_addr[k] + t * d_ts — a slot of ANOTHER rank's halo buffer, mapped into this process (peer
-// memory: torch symmetric memory / cudaIpc).  The pack and the transfer are one kernel: 16-byte
-// stores straight into the peer's HBM, no send buffer, no collective call; the copy engines and
-// NCCL are not involved, and the kernel (no shared memory, 256 threads) co-resides with the
-// persistent hop CTAs, so the exchange of one chunk runs under the SpMM of the other.
-// Small on purpose: 64 threads x 32 registers = 2 K registers per CTA, three of which fit in what the
-// SM has left beside a persistent hop CTA (736 threads x 80 registers = 58.9 K of 64 K) — with 256 threads x 34 registers
-// the first version could not co-reside at all and ran in the gaps between hop launches (58 GB/s).
-// Each thread moves 64 bytes per item with its four loads in flight before the first peer store.
-__global__ void __launch_bounds__(64)
-push_rows_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
-                 const int32_t* __restrict__ index, const int64_t* __restrict__ dst_addr,
-                 int n_index, int64_t d_ts, int F16, int Tc) {
-    // F16 = 64-byte pieces per row
-    const uint32_t per_t = (uint32_t)n_index * (uint32_t)F16;
+// memory: torch symmetric memory).  The pack and the transfer are one kernel: 16-byte stores
+// straight into the peer's HBM, no send buffer, no collective call.
+// Launch shape (256 threads, ~34 registers) measured, not guessed: a 64-thread / 32-register variant
+// that fits beside the persistent hop CTAs (which leave 6.6 K registers per SM) did overlap with the
+// SpMM of the other chunk — and slowed that SpMM by 24 % (its single-thread issue loops share the
+// schedulers), 292 ms per pass at 2 GPUs against 272 ms for this shape, which runs in the gap
+// between two hop launches at NVLink rate.
+__global__ void push_rows_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
+                                 const int32_t* __restrict__ index, const int64_t* __restrict__ dst_addr,
+                                 int n_index, int64_t d_ts, int F4, int Tc) {
+    const uint32_t per_t = (uint32_t)n_index * (uint32_t)F4;
     for (int t = blockIdx.y; t < Tc; t += gridDim.y) {
         const float* sp = src + (size_t)t * s_ts;
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_t; i += gridDim.x * blockDim.x) {
-            const uint32_t k = i / (uint32_t)F16, f = i - k * (uint32_t)F16;
-            const float* rp = sp + (size_t)__ldg(index + k) * s_ns + 16 * f;
-            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(__ldg(dst_addr + k)) + (size_t)t * d_ts + 16 * f);
-            const float4 a = ldg_f4_stream(rp), b = ldg_f4_stream(rp + 4), c = ldg_f4_stream(rp + 8), d = ldg_f4_stream(rp + 12);
-            dp[0] = a; dp[1] = b; dp[2] = c; dp[3] = d;
+            const uint32_t k = i / (uint32_t)F4, f = i - k * (uint32_t)F4;
+            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(__ldg(dst_addr + k)) + (size_t)t * d_ts);
+            dp[f] = ldg_f4_stream(sp + (size_t)__ldg(index + k) * s_ns + 4 * f);
         }
     }
 }
@@ -234,16 +229,16 @@ extern "C" int sgp_push_rows(const float* src, int64_t src_t_stride, int64_t src
                              void* stream) {
     SGP_REQUIRE(src && ((index && dst_addr) || n_index == 0), SGP_EINVAL, "sgp_push_rows: null pointer");
     if (Tc <= 0 || n_index <= 0 || F <= 0) return SGP_OK;
-    SGP_REQUIRE(F % 16 == 0 && aligned16(src) && src_t_stride % 4 == 0 && src_n_stride % 4 == 0 && dst_t_stride % 4 == 0,
-                SGP_EALIGN, "sgp_push_rows: F %% 16 == 0 and 16-byte aligned views required");
-    const int64_t per_t = (int64_t)n_index * (F / 16);
+    SGP_REQUIRE(F % 4 == 0 && aligned16(src) && src_t_stride % 4 == 0 && src_n_stride % 4 == 0 && dst_t_stride % 4 == 0,
+                SGP_EALIGN, "sgp_push_rows: F %% 4 == 0 and 16-byte aligned views required");
+    const int64_t per_t = (int64_t)n_index * (F / 4);
     SGP_REQUIRE(per_t < (1ll << 32), SGP_EUNSUPPORTED, "sgp_push_rows: %d rows x %d features too large", n_index, F);
-    const int gy = Tc < 32 ? Tc : 32;
-    int gx = (int)((per_t + 63) / 64);
-    const int cap = (kNumSMs * 24 + gy - 1) / gy;
+    const int gy = Tc < 64 ? Tc : 64;
+    int gx = (int)((per_t + 255) / 256);
+    const int cap = (kNumSMs * 8 + gy - 1) / gy;
     gx = gx < 1 ? 1 : (gx > cap ? cap : gx);
-    push_rows_kernel<<<dim3(gx, gy), 64, 0, as_stream(stream)>>>(src, src_t_stride, src_n_stride, index, dst_addr,
-                                                                  n_index, dst_t_stride, F / 16, Tc);
+    push_rows_kernel<<<dim3(gx, gy), 256, 0, as_stream(stream)>>>(src, src_t_stride, src_n_stride, index, dst_addr,
+                                                                  n_index, dst_t_stride, F / 4, Tc);
     SGP_LAUNCH_CHECK("push_rows");
     return SGP_OK;
 }
