@@ -131,7 +131,40 @@ class ShiftOperator:
         return out.reshape(*lead, *out.shape[-2:]).to(x.device)
 
 
-Adj = Union[Tensor, np.ndarray, ShiftOperator]
+class SparseAdj:
+    """Minimal stand-in for ``torch_sparse.SparseTensor`` as the reference constructs and passes it
+    (``SparseTensor(row=row, col=col, value=w, sparse_sizes=(N, N))``, lib/sgp_preprocessing.py:81-82):
+    an UN-normalised adjacency in COO form.  ``preprocess_adj`` / ``sgp_spatial_embedding`` /
+    ``sgp_spatial_support`` accept this class and — duck-typed on ``coo()`` + ``sparse_sizes()`` — a
+    real ``torch_sparse.SparseTensor`` when that package is installed."""
+
+    def __init__(self, row: Tensor, col: Tensor, value: Optional[Tensor] = None, sparse_sizes=None):
+        self.row, self.col, self.value = torch.as_tensor(row), torch.as_tensor(col), value
+        n = int(max(int(self.row.max()), int(self.col.max())) + 1) if self.row.numel() else 0
+        self._sizes = tuple(sparse_sizes) if sparse_sizes is not None else (n, n)
+
+    def coo(self):
+        return self.row, self.col, self.value
+
+    def sparse_sizes(self):
+        return self._sizes
+
+    def t(self) -> "SparseAdj":
+        return SparseAdj(self.col, self.row, self.value, self._sizes[::-1])
+
+
+def _is_sparse_adj(obj) -> bool:
+    return not isinstance(obj, (Tensor, np.ndarray)) and hasattr(obj, "coo") and hasattr(obj, "sparse_sizes")
+
+
+def _sparse_to_edges(adj):
+    """A SparseTensor-like adjacency (entry (i, j) = edge j -> i) back to the reference's edge-list
+    convention ``edge_index = [col (source j); row (target i)]`` (``col, row = edge_index``, :80)."""
+    row, col, value = adj.coo()
+    return torch.stack([torch.as_tensor(col), torch.as_tensor(row)]).to(torch.int64), value, int(adj.sparse_sizes()[0])
+
+
+Adj = Union[Tensor, np.ndarray, ShiftOperator, SparseAdj]
 
 
 def _edges_to_device(edge_index, edge_weight, device):
@@ -168,6 +201,9 @@ def preprocess_adj(edge_index: Adj, edge_weight: Optional[Tensor] = None,
     re-normalise; ours is normalised at construction)."""
     if isinstance(edge_index, ShiftOperator):
         return edge_index
+    if _is_sparse_adj(edge_index):                               # the SparseTensor branch (:83-84)
+        edge_index, edge_weight, n = _sparse_to_edges(edge_index)
+        num_nodes = n if num_nodes is None else num_nodes
     if not isinstance(edge_index, (Tensor, np.ndarray)):
         raise RuntimeError("Edge index must be (edge_index, edge_weight) tuple "
                            "or SparseTensor.")
@@ -214,6 +250,8 @@ def make_operators(edge_index, edge_weight, num_nodes, *, undirected, add_self_l
     :205-216)."""
     if undirected:
         assert bidirectional is False
+    if _is_sparse_adj(edge_index):                               # un-normalised SparseTensor-like input
+        edge_index, edge_weight, _ = _sparse_to_edges(edge_index)
     if isinstance(edge_index, ShiftOperator):
         fwd, bwd = edge_index, None
         if bidirectional:
@@ -302,6 +340,9 @@ def sgp_spatial_support(edge_index: Adj, edge_weight=None, num_nodes=None, k=2, 
     """
     if isinstance(edge_index, ShiftOperator):
         raise SgpError("sgp_spatial_support needs the edge list: a built ShiftOperator is already normalised")
+    if _is_sparse_adj(edge_index):
+        edge_index, edge_weight, n = _sparse_to_edges(edge_index)
+        num_nodes = n if num_nodes is None else num_nodes
     if num_nodes is None:
         ei = torch.as_tensor(edge_index)
         num_nodes = int(ei.max()) + 1 if ei.numel() else 0

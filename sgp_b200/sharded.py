@@ -180,9 +180,8 @@ class _NoPhase:
 class PeerHalo:
     """Halo buffers in symmetric memory + per-operator destination address tables for the push."""
 
-    N_LANES = 2
-
-    def __init__(self, operators: List[ShardedOperator], F: int, step: int, device, group):
+    def __init__(self, operators: List[ShardedOperator], F: int, step: int, device, group, n_lanes: int = 2):
+        self.N_LANES = int(n_lanes)
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
@@ -229,13 +228,13 @@ class PeerHalo:
 class RowShardedEncoder:
     """Runs an :class:`sgp_b200.SGPEncoder` on this rank's rows of the graph."""
 
-    N_SLOTS = 3
-
     def __init__(self, encoder, edge_index, edge_weight, num_nodes: int, device, group=None,
-                 exchange: str = "auto"):
+                 exchange: str = "auto", lanes: int = 2):
         """exchange: "p2p" (halo rows pushed into peer-mapped buffers by sgp_push_rows), "nccl"
-        (pack + all_to_all_single), "auto" = p2p when the symmetric-memory rendezvous works."""
+        (pack + all_to_all_single), "auto" = p2p when the symmetric-memory rendezvous works.
+        lanes: hop chains in flight (streams); lanes + 1 chunk buffers."""
         self.enc, self.group, self.dev = encoder, group, torch.device(device)
+        self.N_LANES, self.N_SLOTS = int(lanes), int(lanes) + 1
         self.exchange_mode, self._peer, self._peer_key = exchange, None, None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         spat = encoder.sgp_encoder
@@ -264,7 +263,7 @@ class RowShardedEncoder:
             self.bwd = ShardedOperator(plan_b, self.dev, F, spat.rbu_mode)
         self.op = self.fwd.op                                   # kept: the forward operator
         self.s_scan = torch.cuda.Stream(self.dev)
-        self.s_hop = [torch.cuda.Stream(self.dev) for _ in range(2)]
+        self.s_hop = [torch.cuda.Stream(self.dev) for _ in range(self.N_LANES)]
 
     @property
     def own(self) -> np.ndarray:
@@ -285,7 +284,7 @@ class RowShardedEncoder:
         if self._peer_key != step:
             ok = 1
             try:
-                self._peer = PeerHalo(self.operators, self.F, step, self.dev, self.group)
+                self._peer = PeerHalo(self.operators, self.F, step, self.dev, self.group, self.N_LANES)
             except Exception as e:  # noqa: BLE001 - no peer mapping on this box: fall back together
                 if self.exchange_mode == "p2p":
                     raise
@@ -352,7 +351,7 @@ class RowShardedEncoder:
         lanes = [dict(send=None if peer is not None else torch.empty(max(n_send * step * F, 1), device=dev),
                       halo=None if peer is not None else torch.empty(max(n_halo * step * F, 1), device=dev),
                       sums=torch.empty(step, F, device=dev) if spat.global_attr else None)
-                 for _ in range(2)]
+                 for _ in range(self.N_LANES)]
         main = torch.cuda.current_stream(dev)
         chunks = [(t0, min(T, t0 + step)) for t0 in range(0, T, step)]
         for s in (self.s_scan, *self.s_hop):
@@ -360,7 +359,7 @@ class RowShardedEncoder:
         slot_free: List[Optional[torch.cuda.Event]] = [None] * self.N_SLOTS
         g = spatial_blocks(K, spat.bidirectional)
         for c, (t0, t1) in enumerate(chunks):
-            slot, lane = c % self.N_SLOTS, c % 2
+            slot, lane = c % self.N_SLOTS, c % self.N_LANES
             buf = bufs[slot][: t1 - t0]
             # ---- scan: serial in time (carried state), its own stream ----
             with torch.cuda.stream(self.s_scan):
@@ -513,7 +512,8 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
     torch.cuda.synchronize()
     t_b0 = time.perf_counter()
     import os
-    sh = RowShardedEncoder(enc, ei_t, ew_t, N, dev, exchange=os.environ.get("SGP_B200_EXCHANGE", "auto"))
+    sh = RowShardedEncoder(enc, ei_t, ew_t, N, dev, exchange=os.environ.get("SGP_B200_EXCHANGE", "auto"),
+                           lanes=int(os.environ.get("SGP_B200_LANES", 2)))
     torch.cuda.synchronize()
     build_ms = torch.tensor([(time.perf_counter() - t_b0) * 1e3], device=dev)
     dist.all_reduce(build_ms, op=dist.ReduceOp.MAX)
@@ -625,8 +625,8 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
                         operator_format=("tcgen05 64-row groups" if fmt.tc is not None else
                                          "rbu%d" % fmt.rbu.R if fmt.rbu is not None else "csr"),
                         partition="recursive bisection along the patch diameter (sgp_partition_rows)",
-                        exchange=sh.exchange_used + " of halo rows per hop; scan / 2 hop chains on 3 streams, "
-                                 "3 chunk buffers",
+                        exchange=sh.exchange_used + " of halo rows per hop; scan + %d hop chains on %d streams, "
+                                 "%d chunk buffers" % (sh.N_LANES, sh.N_LANES + 1, sh.N_SLOTS),
                         sink="fp64 checksum of the whole output, accumulated in the scan / hop epilogues"),
                     roofline=roofline,
                     breakdown=dict(

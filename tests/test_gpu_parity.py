@@ -837,3 +837,26 @@ def test_scan_multi_layer_small_reservoirs(H, L, Fin, N, act):
     # and the Reservoir module picks it by itself
     res = sgp_b200.Reservoir(Fin, H, num_layers=L, activation=act)
     assert res.device_plan(torch.device(DEV), N)[0][0] == "multi"
+
+
+def test_sparse_tensor_like_adjacency_input():
+    """preprocess_adj / sgp_spatial_embedding / sgp_spatial_support given the adjacency the way the
+    reference's SparseTensor branch receives it (lib/sgp_preprocessing.py:83-84): an un-normalised
+    COO object with coo() / sparse_sizes()."""
+    n, F = 97, 16
+    ei, ew = random_graph(n, 700, seed=5)
+    adj = sgp_b200.SparseAdj(row=torch.from_numpy(ei[1]), col=torch.from_numpy(ei[0]), value=torch.from_numpy(ew),
+                             sparse_sizes=(n, n))
+    x = np.random.default_rng(2).standard_normal((3, n, F)).astype(np.float32)
+    op = sgp_b200.preprocess_adj(adj, set_diag=True)
+    rowptr, col, val = O.build_operator(ei, ew, n, set_diag=True)
+    np.testing.assert_array_equal(op.csr.col.cpu().numpy(), col)
+    np.testing.assert_allclose(op.csr.val.cpu().numpy(), val, rtol=2e-6)
+    res = sgp_b200.sgp_spatial_embedding(torch.from_numpy(x), n, adj, None, k=2, bidirectional=True)
+    ref = O.spatial_embedding(x, n, ei, ew, k=2, bidirectional=True, impl="c")
+    for a, b in zip(res, ref):
+        assert_blocks_close(a.numpy(), b, F)
+    sup = sgp_b200.sgp_spatial_support(adj, k=2, global_attr=True)
+    want = O.spatial_support_dense(ei, ew, n, k=2, global_attr=True)
+    for a, S in zip(sup, want):
+        assert_blocks_close((a @ torch.from_numpy(x)).numpy(), S @ x.astype(np.float64), F)
