@@ -216,3 +216,45 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["value"] > 0 and "workload" in line["config"]
+
+
+def test_abi_version_matches_header_and_is_checked():
+    lib = _lib.load()
+    assert lib.sgp_version() == _lib.header_abi_version() >= 200
+
+
+def test_chunk_rounding_and_sparse_adj_container():
+    from sgp_b200.preprocessing import SparseAdj, _is_sparse_adj, _sparse_to_edges, round_chunk_steps
+    assert [round_chunk_steps(s, 1000) for s in (1, 3, 4, 5, 16, 19, 1000, 5000)] == [1, 3, 4, 4, 16, 16, 1000, 1000]
+    adj = SparseAdj(row=torch.tensor([1, 2, 2]), col=torch.tensor([0, 0, 1]), value=torch.tensor([1., 2., 3.]))
+    assert adj.sparse_sizes() == (3, 3) and _is_sparse_adj(adj) and not _is_sparse_adj(torch.zeros(2, 3))
+    ei, w, n = _sparse_to_edges(adj)
+    assert n == 3 and ei.tolist() == [[0, 0, 1], [1, 2, 2]] and w.tolist() == [1., 2., 3.]   # [0] = col (source)
+    assert _sparse_to_edges(adj.t())[0].tolist() == [[1, 2, 2], [0, 0, 1]]
+
+
+def test_new_surface_is_exported_and_has_no_cpu_path():
+    for name in ("IIDSampler", "sgp_spatial_support", "sgp_collate_features", "GroupedPointwiseConv",
+                 "GESNEncoder", "GraphESN", "GESNLayer", "SparseAdj", "OperatorChain", "MeanOperator"):
+        assert hasattr(sgp_b200, name), name
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SgpError):
+            sgp_b200.IIDSampler(torch.zeros(10, 3, 4), torch.zeros(10, 3, 1), horizon=2)
+    # GESNEncoder mirrors the reference constructor (lib/nn/encoders/dyn_gesn_encoder.py:11-21)
+    assert list(inspect.signature(sgp_b200.GESNEncoder.__init__).parameters)[1:] == [
+        "input_size", "reservoir_size", "reservoir_layers", "leaking_rate", "spectral_radius", "density",
+        "input_scaling", "alpha_decay", "reservoir_activation"]
+    torch.manual_seed(0)
+    enc = sgp_b200.GESNEncoder(2, 8, 2, 0.9, 0.9, 0.7, 1.0, True)
+    assert [float(c.alpha) for c in enc.reservoir.rnn_cells] == [0.9, float(np.clip(0.9 - 0.1, 0.1, 1.))]
+    p = argparse.ArgumentParser()
+    sgp_b200.GESNEncoder.add_model_specific_args(p)
+    assert p.parse_args(["--reservoir-size", "64", "--alpha-decay"]).alpha_decay is True
+
+
+def test_small_reservoirs_choose_the_fused_multi_layer_plan():
+    torch.manual_seed(0)
+    assert sgp_b200.Reservoir(3, 64, num_layers=2).multi_layer_ok()            # sgp_la.yaml
+    assert sgp_b200.Reservoir(3, 16, num_layers=8).multi_layer_ok()            # sgp_pv.yaml
+    assert not sgp_b200.Reservoir(3, 128, num_layers=1).multi_layer_ok()       # tensor-core / tiled kernels
+    assert not sgp_b200.Reservoir(3, 64, num_layers=8).multi_layer_ok()        # weights exceed shared memory
