@@ -11,8 +11,8 @@ The reference is single-process; this is the B200-side scaling design named by t
 * before each hop the rows of the previous block that other ranks reference ("halo" rows) are
   PUSHED by one kernel (sgp_push_rows) straight into the consumers' halo buffers over NVLink:
   the buffers are torch symmetric memory mapped into every process, the kernel stores 16 bytes
-  per thread to peer addresses, and ONE device-side barrier per hop orders it against the readers
-  (two halo buffers per stream alternate, so a push never overwrites rows a peer may still read).  No send buffer, no second copy, no collective kernel: one pass at NVLink rate in the gap
+  per thread to peer addresses, and a device-side barrier on either side orders it against the
+  readers.  No send buffer, no second copy, no collective kernel: one pass at NVLink rate in the gap
   between two hop launches (measured at 2 GPUs: 272 ms per pass against 291 ms with pack + NCCL
   all-to-all, whose CTAs had to wait for the persistent hop CTAs to leave the SMs anyway).
   ``exchange="nccl"`` keeps the packed all-to-all-v as a fallback where peer mapping is unavailable.  The SpMM kernels read
@@ -191,24 +191,24 @@ class PeerHalo:
         dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=self.group)
         self.slot = step * F                                   # floats per halo row: [step, F]
         self.lane_floats = max(int(n_max) * self.slot, 4)
-        # two buffers per lane, used alternately by consecutive exchanges of the lane: a push may then
-        # overwrite only the buffer read TWO hops ago, which every peer has left (it passed the previous
-        # exchange's barrier after that hop) — one barrier per hop instead of two
-        self.n_bufs = 2 * self.N_LANES
+        # one buffer per lane, a barrier on either side of the push.  (Two alternating buffers per lane
+        # with a single barrier per hop are also correct — a push then only overwrites rows read two
+        # hops ago — but measured 3-4 % slower at 2 and 8 GPUs: the "buffer free" barrier also paces the
+        # pushes into the gaps between hop launches.)
+        self.n_bufs = self.N_LANES
         self.buf = symm_mem.empty(self.n_bufs * self.lane_floats, dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         # every rank's receive layout: recv_counts[p][q] = rows rank p receives from q (its halo is
         # ordered by source rank), so my rows for p start at slot sum(recv_counts[p][:me])
-        self.addr = []                                          # [operator][buffer] -> int64 [n_send] (device)
-        self.seq = [0] * self.N_LANES                           # exchanges issued per lane (buffer parity)
+        self.addr = []                                          # [operator][lane] -> int64 [n_send] (device)
         for o in operators:
             mine = torch.tensor(o.plan.recv_counts, device=device, dtype=torch.int64)
             allc = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allc, mine, group=self.group)
             allc = torch.stack(allc).cpu().numpy()              # [p, q]
             per_lane = []
-            for lane in range(self.n_bufs):                     # buffer index = 2 * lane + parity
+            for lane in range(self.n_bufs):
                 parts = []
                 for p in range(world):
                     n = int(o.plan.send_counts[p])
@@ -302,17 +302,17 @@ class RowShardedEncoder:
         return self._peer
 
     def _exchange_p2p(self, peer: PeerHalo, oi: int, sop: ShardedOperator, block: torch.Tensor, lane: int, phase):
-        """push my rows into the consumers' buffers -> barrier (every push has landed); returns my halo
-        view.  The lane's two buffers alternate, so no "buffer free" barrier is needed (PeerHalo)."""
+        """barrier (every rank is done reading this lane's halo buffer) -> push my rows into the
+        consumers' buffers -> barrier (every push has landed); returns my halo view."""
         Tc = block.shape[0]
-        b = 2 * lane + (peer.seq[lane] & 1)
-        peer.seq[lane] += 1
-        with phase("pack"):
-            if sop.n_send:
-                ops.push_rows(block, sop.send_index, peer.addr[oi][b], self.F)
         with phase("exchange"):
             peer.barrier(lane)
-        return peer.halo_view(b, sop.plan.n_halo, Tc)
+        with phase("pack"):
+            if sop.n_send:
+                ops.push_rows(block, sop.send_index, peer.addr[oi][lane], self.F)
+        with phase("exchange"):
+            peer.barrier(lane)
+        return peer.halo_view(lane, sop.plan.n_halo, Tc)
 
     def _exchange(self, sop: ShardedOperator, block: torch.Tensor, send_flat: torch.Tensor,
                   halo_flat: torch.Tensor, phase):
