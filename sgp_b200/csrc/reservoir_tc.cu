@@ -54,19 +54,6 @@ __device__ __forceinline__ void rt_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  :: "r"(rt_smem_u32(bar)) : "memory");
 }
-// PAIR builds: the commit arrives on the same-offset mbarrier of BOTH CTAs of the cluster
-__device__ __forceinline__ void rt_commit_pair(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 :: "r"(rt_smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ uint32_t rt_cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void rt_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ bool rt_elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
@@ -145,11 +132,7 @@ __device__ __forceinline__ uint32_t rt_lo_part(float v) {
     return __float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u));
 }
 
-// PAIR: the kernel runs as clusters of two CTAs (two node tiles on neighbouring SMs) that share the W
-// stream: every 16 KB image is fetched from L2 ONCE per pair (TMA multicast into both CTAs' rings, the
-// two CTAs issue alternate images) instead of once per SM — the W stream is 5.4 TB/s of L2 -> SM
-// traffic otherwise (profiles/r2_ncu_full_reservoir_tc.txt) and the MMA warp waits on it.
-template <int H, int FINP, int ACT, bool PAIR>
+template <int H, int FINP, int ACT>
 __global__ void __launch_bounds__(kRtThreads, 1)
 reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int Fin,
                     const float* __restrict__ wimg /* [H/32][H/128][2][128*32] */,
@@ -191,7 +174,7 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
         abort_s = 0;
         for (int s = 0; s < kRtWStages; ++s) {
             rt_mbar_init(&wfull[s], 1);           // the producer's arrive.expect_tx; the copy completes the bytes
-            rt_mbar_init(&wempty[s], PAIR ? 2 : 1);     // PAIR: both CTAs' MMAs must be done with the stage
+            rt_mbar_init(&wempty[s], 1);
         }
         for (int i = 0; i < 2; ++i) {
             rt_mbar_init(&acc_ready[i], 1);
@@ -215,8 +198,6 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
-    const uint32_t cta_rank = PAIR ? rt_cluster_ctarank() : 0u;
-    if (PAIR) rt_cluster_sync();        // the partner's barriers are initialised before anything targets them
 
     if (warp == kRtEpiWarps) {
         // ================= producer warp: stream the W images, kStagesPerStep per time step ====
@@ -233,25 +214,12 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
                 const uint32_t bar = rt_smem_u32(&wfull[s]);
                 asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n"
                              :: "r"(bar), "r"(kRtWStage) : "memory");
-                if (!PAIR) {
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 :: "r"(w_base + s * kRtWStage), "l"(src), "r"(kRtWStage), "r"(bar) : "memory");
-                } else if ((uint32_t)(j & 1) == cta_rank) {
-                    // my turn: ONE L2 read, delivered to the same ring stage (and wfull barrier) of both CTAs
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-                                 "[%0], [%1], %2, [%3], %4;"
-                                 :: "r"(w_base + s * kRtWStage), "l"(src), "r"(kRtWStage), "r"(bar), "h"((uint16_t)3) : "memory");
-                }
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(w_base + s * kRtWStage), "l"(src), "r"(kRtWStage), "r"(bar) : "memory");
             }
             __syncwarp();
             if (++s == kRtWStages) { s = 0; ++ph; }
             if (++js == kStagesPerStep) js = 0;
-        }
-        if (PAIR) {
-            // the partner's last commits arrive on MY wempty barriers: wait for them before leaving, so
-            // that nothing targets this CTA's shared memory after it has exited
-            for (long long u = total > kRtWStages ? total - kRtWStages : 0; u < total; ++u)
-                if (!rt_wait(&wempty[u % kRtWStages], (uint32_t)((u / kRtWStages) & 1), &abort_s, err, lane)) break;
         }
     } else if (warp < kRtEpiWarps) {
         // ================= epilogue warps: thread = node, warp = (lane quarter, column group) ==
@@ -435,7 +403,7 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
                             mma_ss(dcol, da, db, idesc, (c | ks) ? 1u : 0u);
                             mma_ts(dcol, tmem_d + ALO_OFF + c * 32 + ks * 8, db, idesc, 1u);
                         }
-                        if (PAIR) rt_commit_pair(&wempty[s]); else rt_commit(&wempty[s]);
+                        rt_commit(&wempty[s]);
                     }
                     __syncwarp();
                     if (++s == kRtWStages) { s = 0; ++ph; }
@@ -451,7 +419,7 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
                             const uint64_t db = desc(wl + ks * 2, hi32);
                             mma_ss(dcol, da, db, idesc, 1u);
                         }
-                        if (PAIR) rt_commit_pair(&wempty[s]); else rt_commit(&wempty[s]);
+                        rt_commit(&wempty[s]);
                         // the epilogue may overwrite state chunks once these fire: the output
                         // stores must have read them (issued >10k cycles ago)
                         if (hh == NH - 1 && (c < NFREE || c == NC - 1))
@@ -482,7 +450,6 @@ reservoir_tc_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, int
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(TMEM_COLS));
-    if (PAIR) rt_cluster_sync();        // neither CTA leaves while the other may still multicast into it
 }
 
 // W_hh [H, H] -> images [H/32 chunks][H/128 halves][hi | lo][128 n x 32 k, K-major SWIZZLE_128B]
@@ -561,31 +528,12 @@ extern "C" int sgp_reservoir_scan_tc(const float* x, int64_t x_t_stride, int64_t
 #else
     long long* trace_ptr = nullptr;
 #endif
-    // CTA pairs sharing the W stream (TMA multicast) when there are at least two tiles; SGP_B200_RT_PAIR=0
-    // (read once) selects the single-CTA kernel
-    static const bool pair_knob = !(getenv("SGP_B200_RT_PAIR") && getenv("SGP_B200_RT_PAIR")[0] == '0');
-    const bool pair = pair_knob && grid >= 2;
-    const int grid_pair = (grid + 1) & ~1;               // an odd tile count gets one idle tile (all nodes >= N)
 #define SGP_RT(H_, F_, A_)                                                                              \
     do {                                                                                                \
-        if (pair) {                                                                                     \
-            auto kern = reservoir_tc_kernel<H_, F_, A_, true>;                                          \
-            SGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            cudaLaunchConfig_t cfg = {};                                                                \
-            cfg.gridDim = dim3(grid_pair); cfg.blockDim = dim3(kRtThreads);                             \
-            cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);                                \
-            cudaLaunchAttribute attr[1];                                                                \
-            attr[0].id = cudaLaunchAttributeClusterDimension;                                           \
-            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;   \
-            cfg.attrs = attr; cfg.numAttrs = 1;                                                         \
-            SGP_CUDA(cudaLaunchKernelEx(&cfg, kern, x, x_t_stride, x_n_stride, Fin, wimg, w_ih, bias, alpha, \
-                                        one_minus_alpha, h_state, out_map, Tc, N, err_flag, checksum, trace_ptr)); \
-        } else {                                                                                        \
-            SGP_CUDA(cudaFuncSetAttribute(reservoir_tc_kernel<H_, F_, A_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            reservoir_tc_kernel<H_, F_, A_, false><<<grid, kRtThreads, smem, as_stream(stream)>>>(      \
-                x, x_t_stride, x_n_stride, Fin, wimg, w_ih, bias, alpha, one_minus_alpha, h_state, out_map, \
-                Tc, N, err_flag, checksum, trace_ptr);                                                  \
-        }                                                                                               \
+        SGP_CUDA(cudaFuncSetAttribute(reservoir_tc_kernel<H_, F_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        reservoir_tc_kernel<H_, F_, A_><<<grid, kRtThreads, smem, as_stream(stream)>>>(                 \
+            x, x_t_stride, x_n_stride, Fin, wimg, w_ih, bias, alpha, one_minus_alpha, h_state, out_map, \
+            Tc, N, err_flag, checksum, trace_ptr);                                                      \
     } while (0)
 #define SGP_RT_F(H_, A_)                                                                                \
     do {                                                                                                \
