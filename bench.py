@@ -371,7 +371,7 @@ def run_own(args, cfg):
                     gflops=flops_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0,
                     fp32_fma_peak_tflops=fma_peak,
                     share_of_step=spmm_ms / (args.steps * ms_step) if ms_step else None)
-    reservoir = dict(kernel={"tc": "reservoir_tc_kernel (tcgen05, 3xTF32)", "multi": "reservoir_scan_small (all layers, one launch)",
+    reservoir = dict(kernel={"tc": "reservoir_tc_kernel (tcgen05, 3xTF32)", "tc16": "reservoir_tc16_kernel (tcgen05, fp16x3)", "multi": "reservoir_scan_small (all layers, one launch)",
                              "cuda": "reservoir_scan_tiled / generic"}[plan[0][0]], ms_per_step=scan_ms / args.steps,
                      tflops=scan_flops / (scan_ms * 1e-3) / 1e12 if scan_ms else 0.0,
                      frac_of_fp32_fma_peak=(scan_flops / (scan_ms * 1e-3) / 1e12) / fma_peak if scan_ms else 0.0,

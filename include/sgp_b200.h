@@ -130,6 +130,19 @@ int sgp_reservoir_scan_tc(const float* x, int64_t x_t_stride, int64_t x_n_stride
                           float* h_state, float* out, int64_t out_t_stride, int64_t out_n_stride,
                           int Tc, int N, int H, int* err_flag, double* checksum /*nullable*/, void* stream);
 
+/* Tensor-core scan with fp16x3 operands (tcgen05 kind::f16: twice the tf32 MMA rate, half the W
+ * stream; same 22-bit split accuracy): same contract as sgp_reservoir_scan_tc for TANH reservoirs
+ * whose states stay within [-1, 1] (zero or bounded initial state: tanh + leaky blend keep them
+ * there).  w_scale = the power of two that brings max|W_hh| into [2^13, 2^14) (fp16 normal range;
+ * chosen by the caller, passed to both calls); wimg [2*H*H] fp16 (sgp_reservoir_tc16_pack). */
+int sgp_reservoir_tc16_pack(const float* w_hh /*[H,H]*/, int H, float w_scale, void* wimg /*fp16 [2*H*H]*/,
+                            void* stream);
+int sgp_reservoir_scan_tc16(const float* x, int64_t x_t_stride, int64_t x_n_stride, int Fin,
+                            const void* wimg, float w_scale, const float* w_ih, const float* bias,
+                            float alpha, float one_minus_alpha,
+                            float* h_state, float* out, int64_t out_t_stride, int64_t out_n_stride,
+                            int Tc, int N, int H, int* err_flag, double* checksum /*nullable*/, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2  CSR x dense propagation, batched over the leading (time / batch) axis.
  * Replaces `x = adj @ x` (lib/sgp_preprocessing.py:200-203; torch_sparse spmm_sum):

@@ -37,6 +37,10 @@ SIGNATURES = {
     "sgp_reservoir_scan_tc": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_float,
                                       c_float, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                       c_int, c_void_p, c_void_p, c_void_p]),
+    "sgp_reservoir_tc16_pack": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "sgp_reservoir_scan_tc16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                        c_float, c_float, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p]),
     "sgp_spmm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                          c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "sgp_spmm_halo": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,

@@ -156,6 +156,33 @@ def reservoir_scan_tc(x: torch.Tensor, wimg: torch.Tensor, w_ih: torch.Tensor, b
                                        out.stride(0), out.stride(1), Tc, N, H, _p(err), _p(checksum), _stream(x.device))
 
 
+def reservoir_tc16_pack(w_hh: torch.Tensor):
+    """W_hh [H, H] -> (fp16 hi / lo images for the fp16x3 tensor-core scan, the power-of-two weight scale)."""
+    _require_cuda(w_hh)
+    H = int(w_hh.shape[0])
+    wmax = float(w_hh.abs().max())
+    scale = float(2.0 ** np.floor(np.log2(16384.0 / wmax))) if wmax > 0 else 1.0
+    out = torch.empty(2 * H * H, dtype=torch.float16, device=w_hh.device)
+    _call(w_hh.device, "sgp_reservoir_tc16_pack", _p(w_hh.contiguous()), H, scale, _p(out), _stream(w_hh.device))
+    return out, scale
+
+
+def reservoir_scan_tc16(x: torch.Tensor, wimg: torch.Tensor, w_scale: float, w_ih: torch.Tensor, bias: torch.Tensor,
+                        alpha: float, h_state: torch.Tensor, out: torch.Tensor, err: torch.Tensor,
+                        checksum: Optional[torch.Tensor] = None) -> None:
+    """fp16x3 tensor-core scan (tanh, states within [-1, 1]); same views as reservoir_scan_tc."""
+    _require_cuda(x, wimg, w_ih, bias, h_state, out, err)
+    _check_view3(x, "x")
+    _check_view3(out, "out")
+    Tc, N, Fin = x.shape
+    H = int(bias.numel())
+    assert out.shape == (Tc, N, H) and h_state.shape == (N, H) and h_state.is_contiguous()
+    a = float(alpha)
+    _call(x.device, "sgp_reservoir_scan_tc16", _p(x), x.stride(0), x.stride(1), Fin, _p(wimg), float(w_scale), _p(w_ih),
+          _p(bias), a, float(1.0 - a), _p(h_state), _p(out), out.stride(0), out.stride(1), Tc, N, H, _p(err),
+          _p(checksum), _stream(x.device))
+
+
 def spmm(csr: Csr, src: torch.Tensor, dst: torch.Tensor, row_order: Optional[torch.Tensor] = None,
          n_rows: Optional[int] = None, halo: Optional[torch.Tensor] = None, n_split: int = 0) -> None:
     _require_cuda(src, dst, csr.rowptr, halo)

@@ -91,6 +91,17 @@ class ReservoirLayer(nn.Module):
         return (self.hidden_size in (128, 256) and self.w_ih.shape[1] <= 8 and
                 self.activation_name in ("tanh", "relu"))
 
+    def device_weights_tc16(self, device):
+        """(fp16 wimg, w_scale, w_ih [H, Fin], bias [H]) for the fp16x3 tensor-core scan."""
+        w_ih = self.w_ih.detach().to(device=device, dtype=torch.float32).contiguous()
+        w_hh = self.w_hh.detach().to(device=device, dtype=torch.float32)
+        if self.b_ih is not None:
+            b = self.b_ih.detach().to(device=device, dtype=torch.float32).contiguous()
+        else:
+            b = torch.zeros(self.hidden_size, device=device)
+        wimg, scale = ops.reservoir_tc16_pack(w_hh)
+        return wimg, scale, w_ih, b
+
     def device_weights_tc(self, device):
         """(wimg, w_ih [H, Fin], bias [H]) for the tensor-core scan."""
         w_ih = self.w_ih.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -144,13 +155,16 @@ class Reservoir(nn.Module):
             layer.reset_parameters()
 
     # ---- device-side execution ------------------------------------------------------------
-    # tensor-core scan: "auto" (node count >= 2048 and the layer qualifies) | "tc" | "cuda" |
+    # tensor-core scan: "auto" (node count >= 2048 and the layer qualifies: fp16x3 for tanh, else
+    # 3xTF32) | "tc16" | "tc" (3xTF32 always) | "cuda" |
     # "layerwise" (as "cuda", and small reservoirs also run one launch per layer)
     tc_mode = os.environ.get("SGP_B200_RESERVOIR", "auto")
 
-    def device_plan(self, device, num_nodes: Optional[int] = None) -> List[tuple]:
-        """Per layer ("cuda", wpack, bias, alpha) or ("tc", wimg, w_ih, bias, alpha, err_flag),
-        uploaded/packed for `device`."""
+    def device_plan(self, device, num_nodes: Optional[int] = None, bounded_state: bool = True) -> List[tuple]:
+        """Per layer ("cuda", wpack, bias, alpha), ("tc", wimg, w_ih, bias, alpha, err_flag) or
+        ("tc16", wimg16, w_scale, w_ih, bias, alpha, err_flag), uploaded/packed for `device`; one
+        ("multi", ...) entry for small reservoirs.  `bounded_state`: the carried state is known to
+        stay within [-1, 1] (zero initial state + tanh), which the fp16x3 scan requires."""
         if self.multi_layer_ok(device):
             ws = [(l.w_ih.detach().to(device=device, dtype=torch.float32).contiguous(),
                    l.w_hh.detach().to(device=device, dtype=torch.float32).contiguous(),
@@ -161,8 +175,11 @@ class Reservoir(nn.Module):
         plan = []
         for layer in self.reservoir_layers:
             use_tc = layer.tensor_core_ok() and (
-                self.tc_mode == "tc" or (self.tc_mode == "auto" and (num_nodes or 0) >= 2048))
-            if use_tc:
+                self.tc_mode in ("tc", "tc16") or (self.tc_mode == "auto" and (num_nodes or 0) >= 2048))
+            if use_tc and self.tc_mode in ("auto", "tc16") and layer.activation_name == "tanh" and bounded_state:
+                plan.append(("tc16", *layer.device_weights_tc16(device), float(layer.alpha),
+                             torch.zeros(1, dtype=torch.int32, device=device)))
+            elif use_tc:
                 plan.append(("tc", *layer.device_weights_tc(device), float(layer.alpha),
                              torch.zeros(1, dtype=torch.int32, device=device)))
             else:
@@ -195,7 +212,10 @@ class Reservoir(nn.Module):
             return
         for l, entry in enumerate(plan):
             blk = out[..., l * H:(l + 1) * H]
-            if entry[0] == "tc":
+            if entry[0] == "tc16":
+                _, wimg, w_scale, w_ih, b, alpha, err = entry
+                ops.reservoir_scan_tc16(inp, wimg, w_scale, w_ih, b, alpha, h_state[l], blk, err, checksum)
+            elif entry[0] == "tc":
                 _, wimg, w_ih, b, alpha, err = entry
                 ops.reservoir_scan_tc(inp, wimg, w_ih, b, alpha, self.mode, h_state[l], blk, err, checksum)
             else:
@@ -209,7 +229,7 @@ class Reservoir(nn.Module):
     def check_plan(plan) -> None:
         """Raise if a tensor-core scan reported a barrier timeout (synchronises)."""
         for entry in plan:
-            if entry[0] == "tc" and int(entry[-1].item()) != 0:
+            if entry[0] in ("tc", "tc16") and int(entry[-1].item()) != 0:
                 raise SgpError("sgp_reservoir_scan_tc: internal barrier timed out (results invalid)")
 
     def forward(self, x, h0=None, return_last_state=False):
@@ -217,7 +237,7 @@ class Reservoir(nn.Module):
         B, S, N, Fin = x.size()
         dev = _cuda_device_for(x)
         L, H = len(self.reservoir_layers), self.hidden_size
-        plan = self.device_plan(dev, B * N)
+        plan = self.device_plan(dev, B * N, bounded_state=h0 is None)
         # 'b s n f -> s (b n) f'
         xd = x.detach().to(device=dev, dtype=torch.float32).permute(1, 0, 2, 3).reshape(S, B * N, Fin)
         xd = xd.contiguous()

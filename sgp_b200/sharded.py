@@ -419,7 +419,7 @@ class RowShardedEncoder:
             if sop.op.tc is not None:
                 bad |= int(sop.op.tc.err.item() != 0)
         for entry in getattr(self, "_plan_for_check", []) or []:
-            if entry[0] == "tc":
+            if entry[0] in ("tc", "tc16"):
                 bad |= int(entry[-1].item() != 0)
         flag = torch.tensor([bad], device=self.dev, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)

@@ -511,7 +511,7 @@ def test_sgp_encoder_baseline_shapes_vs_oracle(c):
     # which kernels the dispatch picks for this shape (deterministic: same calls as forward makes)
     fwd, bwd = enc.sgp_encoder.build_operators(torch.from_numpy(ei), torch.from_numpy(ew), N, torch.device(DEV), H)
     plan = enc.reservoir.device_plan(torch.device(DEV), N)
-    assert (fwd.tc is not None) == c["tc"] and (plan[0][0] == "tc") == c["tc"]
+    assert (fwd.tc is not None) == c["tc"] and (plan[0][0] in ("tc", "tc16")) == c["tc"]
     assert (bwd is not None) == bidir and (bwd is None or (bwd.tc is not None) == c["tc"])
     del fwd, bwd, plan
     ref = O.sgp_encoder(x, ei, ew, _layers_of(enc), "tanh", K, bidir, und, glob, add_self_loops=loops,
@@ -860,3 +860,69 @@ def test_sparse_tensor_like_adjacency_input():
     want = O.spatial_support_dense(ei, ew, n, k=2, global_attr=True)
     for a, S in zip(sup, want):
         assert_blocks_close((a @ torch.from_numpy(x)).numpy(), S @ x.astype(np.float64), F)
+
+
+# ---------------------------------------------------------------- K1-TC16: fp16x3 tensor-core scan
+def run_scan_tc16(x, layer, chunk=None):
+    """Drive sgp_reservoir_scan_tc16 (tcgen05 kind::f16, fp16x3) for one tanh layer."""
+    x = torch.as_tensor(x, device=DEV)
+    T, N, _ = x.shape
+    H = layer["w_hh"].shape[0]
+    out = torch.empty(T, N, H, device=DEV)
+    state = torch.zeros(N, H, device=DEV)
+    wimg, scale = ops.reservoir_tc16_pack(layer["w_hh"].to(DEV))
+    w_ih, b = layer["w_ih"].to(DEV).contiguous(), layer["b_ih"].to(DEV)
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    step = chunk or T
+    for t0 in range(0, T, step):
+        ops.reservoir_scan_tc16(x[t0:t0 + step], wimg, scale, w_ih, b, layer["alpha"], state, out[t0:t0 + step], err)
+    assert int(err.item()) == 0, "fp16x3 tensor-core scan reported a barrier timeout"
+    return out.cpu().numpy(), state.cpu().numpy()
+
+
+@pytest.mark.parametrize("H,N,Fin", [(256, 300, 1), (256, 129, 3), (128, 700, 3), (128, 64, 2), (256, 1000, 8)])
+def test_scan_fp16x3_vs_oracle(H, N, Fin):
+    torch.manual_seed(H + N + Fin)
+    layers = O.draw_reservoir(Fin, H, 1, 0.9, 0.9, 0.7)
+    x = np.random.default_rng(N).standard_normal((50, N, Fin)).astype(np.float32)
+    ref = O.reservoir_states(x, layers, "tanh", dtype=torch.float64).numpy()
+    y, st = run_scan_tc16(x, layers[0])
+    ok, worst = O.blockwise_allclose(y, ref, H)
+    if not ok:
+        e = np.abs(y - ref)
+        t, n, c = np.unravel_index(int(e.argmax()), e.shape)
+        raise AssertionError(f"worst |err|/tol = {worst:.3g}; max |err| {e.max():.3e} at t={t} node={n} col={c}; "
+                             f"errors by step {np.round(e.max(axis=(1, 2))[:8], 7)}; by column block of 32 at t=0 "
+                             f"{np.round(e[0].reshape(N, H // 32, 32).max(axis=(0, 2)), 6)}")
+    np.testing.assert_array_equal(st, y[-1])
+    part, st2 = run_scan_tc16(x, layers[0], chunk=7)               # state carried across chunks: bit-identical
+    np.testing.assert_array_equal(part, y)
+    np.testing.assert_array_equal(st2, st)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.endswith("_tc")])
+def test_scan_fp16x3_vs_reference_golden(name):
+    """The fp16x3 scan against outputs of the UNMODIFIED reference reservoir (tests/golden/make_golden.py)."""
+    g = load_golden(name)
+    assert g["kwargs"].get("activation", "tanh") == "tanh"
+    y, _ = run_scan_tc16(g["x"], g["layers"][0])
+    assert_blocks_close(y, g["y"], g["kwargs"]["hidden_size"])
+
+
+def test_scan_fp16x3_long_recurrence_and_weight_ranges():
+    """1000 steps at H = 256 against float64 (round-to-nearest fp16 splits: as accurate as 3xTF32), and
+    weights far from the default scale (spectral radius 0.1 / 3.0: the power-of-two weight scale)."""
+    torch.manual_seed(9)
+    layers = O.draw_reservoir(1, 256, 1, 0.9, 0.9, 0.7)
+    x = sensor_signal(1000, 130, seed=4, exogenous=False)
+    ref = O.reservoir_states(x, layers, "tanh", dtype=torch.float64).numpy()
+    y, _ = run_scan_tc16(x, layers[0])
+    assert_blocks_close(y[-50:], ref[-50:], 256)
+    assert float(np.abs(y - ref).max()) < 5e-6
+    for rho in (0.1, 3.0):
+        torch.manual_seed(3)
+        layers = O.draw_reservoir(2, 128, 1, 0.7, rho, 0.5)
+        x = sensor_signal(60, 200, seed=2)[..., :2]
+        ref = O.reservoir_states(x, layers, "tanh", dtype=torch.float64).numpy()
+        y, _ = run_scan_tc16(x, layers[0])
+        assert_blocks_close(y, ref, 128)
