@@ -911,7 +911,9 @@ def test_scan_fp16x3_vs_reference_golden(name):
 
 def test_scan_fp16x3_long_recurrence_and_weight_ranges():
     """1000 steps at H = 256 against float64 (round-to-nearest fp16 splits: as accurate as 3xTF32), and
-    weights far from the default scale (spectral radius 0.1 / 3.0: the power-of-two weight scale)."""
+    weights far from the default scale (tiny: spectral radius 0.05; large: a 5 %-dense matrix whose
+    entries reach 0.6 at spectral radius 0.9 — contractive, unlike a large radius): the power-of-two
+    weight scale follows max|W|."""
     torch.manual_seed(9)
     layers = O.draw_reservoir(1, 256, 1, 0.9, 0.9, 0.7)
     x = sensor_signal(1000, 130, seed=4, exogenous=False)
@@ -919,10 +921,11 @@ def test_scan_fp16x3_long_recurrence_and_weight_ranges():
     y, _ = run_scan_tc16(x, layers[0])
     assert_blocks_close(y[-50:], ref[-50:], 256)
     assert float(np.abs(y - ref).max()) < 5e-6
-    for rho in (0.1, 3.0):
+    for rho, density in ((0.05, 0.5), (0.9, 0.05)):
         torch.manual_seed(3)
-        layers = O.draw_reservoir(2, 128, 1, 0.7, rho, 0.5)
+        layers = O.draw_reservoir(2, 128, 1, 0.7, rho, density)
         x = sensor_signal(60, 200, seed=2)[..., :2]
         ref = O.reservoir_states(x, layers, "tanh", dtype=torch.float64).numpy()
         y, _ = run_scan_tc16(x, layers[0])
-        assert_blocks_close(y, ref, 128)
+        ok, worst = O.blockwise_allclose(y, ref, 128)
+        assert ok, f"rho={rho} density={density} max|W|={float(layers[0]['w_hh'].abs().max()):.3g}: worst |err|/tol = {worst:.3g}"
