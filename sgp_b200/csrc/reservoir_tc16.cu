@@ -35,7 +35,10 @@ namespace sgp {
 constexpr int kR16EpiWarps = 16;
 constexpr int kR16Threads = (kR16EpiWarps + 2) * 32;
 constexpr int kR16WStage = 128 * 64 * 2;     // 16 KB: one [128 n x 64 k] fp16 image (hi OR lo)
-constexpr int kR16WStages = 5;
+#ifndef SGP_R16_STAGES
+#define SGP_R16_STAGES 5
+#endif
+constexpr int kR16WStages = SGP_R16_STAGES;
 constexpr int kR16MaxFin = 8;
 constexpr int kR16OutTile = 32 * 32 * 4;     // 4 KB per epilogue warp
 constexpr float kR16StateScale = 16384.f;    // 2^14
@@ -104,24 +107,13 @@ __device__ __forceinline__ float r16_tanh(float x) {      // as in reservoir_tc.
 __device__ __forceinline__ uint32_t a16_offset(int m, int k) {
     return (uint32_t)((k >> 6) * 16384 + (m >> 3) * 1024 + (m & 7) * 128 + ((((k & 63) >> 3) ^ (m & 7)) << 4) + (k & 7) * 2);
 }
-// two fp16 packed in a TMEM cell: element 2j in the low half, 2j + 1 in the high half
-__device__ __forceinline__ uint32_t r16_pack(__half a, __half b) {
-    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-// the same for the TMEM A operand (bring-up switch: -DSGP_R16_PACK_SWAP puts element 2j in the high half)
-__device__ __forceinline__ uint32_t r16_pack_tmem(__half a, __half b) {
-#ifdef SGP_R16_PACK_SWAP
-    return r16_pack(b, a);
-#else
-    return r16_pack(a, b);
-#endif
-}
-__device__ __forceinline__ float r16_unpack_tmem(uint32_t w, int odd) {
-#ifdef SGP_R16_PACK_SWAP
-    odd ^= 1;
-#endif
-    return __half2float(__ushort_as_half((unsigned short)(odd ? (w >> 16) : (w & 0xffffu))));
-}
+// fp16 pairs, in shared memory and in a TMEM cell alike: element 2j in the low half, 2j + 1 in the high
+// half (validated on hardware: the swapped order is 5e-4 off).  All fp32 <-> fp16 conversions are the
+// PACKED ones (cvt.rn.f16x2.f32 = F2FP, full rate): the scalar F2F conversions of the first version
+// ran on the XU pipe next to the two MUFU ops of every tanh and made the epilogue XU-bound (49 % of
+// the pipe's peak over the whole launch, profiles/r2_ncu_full_reservoir_tc16.txt).
+__device__ __forceinline__ uint32_t r16_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __half2 r16_half2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
 
 template <int H, int FINP>
 __global__ void __launch_bounds__(kR16Threads, 1)
@@ -218,9 +210,10 @@ reservoir_tc16_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, i
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
                     const float s0 = hn[j + e] * kR16StateScale, s1 = hn[j + e + 1] * kR16StateScale;
-                    const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
-                    hp[e >> 1] = r16_pack(h0, h1);
-                    lo[(j + e) >> 1] = r16_pack_tmem(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)));
+                    const __half2 h2 = __floats2half2_rn(s0, s1);
+                    const float2 hf = __half22float2(h2);
+                    hp[e >> 1] = r16_bits(h2);
+                    lo[(j + e) >> 1] = r16_bits(__floats2half2_rn(s0 - hf.x, s1 - hf.y));
                 }
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};"
                              :: "r"(a_base + a16_offset(m, c * 64 + ko + j)), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]), "r"(hp[3]) : "memory");
@@ -253,7 +246,7 @@ reservoir_tc16_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, i
         bool ok = true;
         bool store_pending = false;
         double csum = 0.0;
-        constexpr float kInvState = 1.f / kR16StateScale;
+        const float oma_s = oma * (1.f / kR16StateScale);      // exact: a power of two
         for (int t = 0; t < Tc && ok; ++t) {
             float xn[FINP];
 #pragma unroll
@@ -278,15 +271,24 @@ reservoir_tc16_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, i
                     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                                  : "=r"(hp[0]), "=r"(hp[1]), "=r"(hp[2]), "=r"(hp[3]) : "r"(a_base + a16_offset(m, c0 + j)));
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const uint32_t hw = hp[e >> 1], lw = lo_old[(j + e) >> 1];
-                        const float hi_f = __half2float(__ushort_as_half((unsigned short)((e & 1) ? (hw >> 16) : (hw & 0xffffu))));
-                        const float lo_f = r16_unpack_tmem(lw, e & 1);
-                        const float h_old = (hi_f + lo_f) * kInvState;
-                        float z = fmaf(__uint_as_float(d[j + e]), inv_scale, bias_s[c0 + j + e]);
+                    for (int e = 0; e < 8; e += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j + e);
+                        float z[4] = {fmaf(__uint_as_float(d[j + e]), inv_scale, b4.x), fmaf(__uint_as_float(d[j + e + 1]), inv_scale, b4.y),
+                                      fmaf(__uint_as_float(d[j + e + 2]), inv_scale, b4.z), fmaf(__uint_as_float(d[j + e + 3]), inv_scale, b4.w)};
 #pragma unroll
-                        for (int f = 0; f < FINP; ++f) z = fmaf(xr[f], wih_s[f * H + c0 + j + e], z);
-                        hn[j + e] = fmaf(alpha, r16_tanh(z), oma * h_old);
+                        for (int f = 0; f < FINP; ++f) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wih_s + f * H + c0 + j + e);
+                            z[0] = fmaf(xr[f], w4.x, z[0]); z[1] = fmaf(xr[f], w4.y, z[1]);
+                            z[2] = fmaf(xr[f], w4.z, z[2]); z[3] = fmaf(xr[f], w4.w, z[3]);
+                        }
+#pragma unroll
+                        for (int p2 = 0; p2 < 4; p2 += 2) {
+                            // old state = (hi + lo) / 2^14, folded into the blend: oma_s = (1 - alpha) / 2^14
+                            const float2 hf = __half22float2(r16_half2(hp[(e + p2) >> 1]));
+                            const float2 lf = __half22float2(r16_half2(lo_old[(j + e + p2) >> 1]));
+                            hn[j + e + p2] = fmaf(oma_s, hf.x, fmaf(oma_s, lf.x, alpha * r16_tanh(z[p2])));
+                            hn[j + e + p2 + 1] = fmaf(oma_s, hf.y, fmaf(oma_s, lf.y, alpha * r16_tanh(z[p2 + 1])));
+                        }
                     }
                 }
                 if (live) {
