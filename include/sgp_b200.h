@@ -207,6 +207,12 @@ int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int
                     float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
                     int F, int Tc, int* err_flag, double* checksum /*nullable*/, void* stream);
 
+/* Process-wide limit on the persistent CTAs of sgp_spmm_rbu_tc (default and maximum: one per SM, 148).
+ * The row-sharded encoder lowers it on >= 4 GPUs so that a few SMs stay free for the halo push and
+ * the barrier kernels, which cannot share an SM with a hop CTA (registers) and would otherwise wait
+ * for the gap between two hop launches. */
+int sgp_tc_set_cta_limit(int n_ctas);
+
 /* HOST function (pointers are host memory, no stream): choose the R-row groups of the RBU format
  * from a CSR operator by a breadth-first, heaviest-neighbour-first greedy (group_rows.cu).
  * grp_rows must hold ceil(N/R)*R entries; unused slots of the last group are set to -1. */

@@ -582,7 +582,15 @@ const TcKnobs& tc_knobs() {
     static const TcKnobs k;
     return k;
 }
+// persistent CTAs per launch (<= one per SM); see sgp_tc_set_cta_limit
+std::atomic<int> g_tc_cta_limit{sgp::kNumSMs};
 }  // namespace
+
+extern "C" int sgp_tc_set_cta_limit(int n_ctas) {
+    SGP_REQUIRE(n_ctas >= 1, SGP_EINVAL, "sgp_tc_set_cta_limit: n_ctas=%d", n_ctas);
+    g_tc_cta_limit.store(n_ctas < sgp::kNumSMs ? n_ctas : sgp::kNumSMs, std::memory_order_relaxed);
+    return SGP_OK;
+}
 
 extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int32_t* cols,
                                const float* bimg, int n_groups, const float* src, int64_t src_t_stride,
@@ -612,7 +620,8 @@ extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows
     const int n_work = n_groups * ny;
     const int group_major = tc_knobs().group_major, gather_policy = tc_knobs().gather_policy;
     const int n_par = group_major ? n_groups : n_work;
-    const int grid = n_par < kNumSMs ? n_par : kNumSMs;          // persistent: one CTA per SM
+    const int cta_limit = g_tc_cta_limit.load(std::memory_order_relaxed);
+    const int grid = n_par < cta_limit ? n_par : cta_limit;      // persistent: one CTA per SM (or fewer: row-sharded runs)
 #ifdef SGP_TC_TRACE
     // trace builds only (tools/trace_tc.py): device buffer for the per-item timestamps of one CTA
     long long* trace_ptr = getenv("SGP_B200_TC_TRACE") ? (long long*)strtoull(getenv("SGP_B200_TC_TRACE"), nullptr, 10) : nullptr;

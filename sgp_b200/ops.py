@@ -383,6 +383,11 @@ def spmm_tc(tc: TcOp, src: torch.Tensor, dst: torch.Tensor, halo: Optional[torch
                                  _stream(src.device))
 
 
+def tc_set_cta_limit(n_ctas: int) -> None:
+    """Persistent CTAs per tensor-core hop launch (process-wide; 148 = one per SM)."""
+    check(load().sgp_tc_set_cta_limit(int(n_ctas)), "sgp_tc_set_cta_limit")
+
+
 def tc_check(tc: TcOp) -> None:
     """Raise if a tensor-core launch reported an internal barrier timeout (synchronises)."""
     if int(tc.err.item()) != 0:

@@ -240,6 +240,11 @@ class RowShardedEncoder:
         lanes: hop chains in flight (streams); lanes + 1 chunk buffers."""
         self.enc, self.group, self.dev = encoder, group, torch.device(device)
         self.N_LANES, self.N_SLOTS = int(lanes), int(lanes) + 1
+        # SMs left free for the halo push / barrier kernels (they cannot share an SM with a hop CTA)
+        import os
+        free = os.environ.get("SGP_B200_FREE_SMS")
+        self.free_sms = int(free) if free is not None else 0
+        ops.tc_set_cta_limit(148 - self.free_sms)
         self.exchange_mode, self._peer, self._peer_key = exchange, None, None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         spat = encoder.sgp_encoder
@@ -631,7 +636,7 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
                                          "rbu%d" % fmt.rbu.R if fmt.rbu is not None else "csr"),
                         partition="recursive bisection along the patch diameter (sgp_partition_rows)",
                         exchange=sh.exchange_used + " of halo rows per hop; scan + %d hop chains on %d streams, "
-                                 "%d chunk buffers" % (sh.N_LANES, sh.N_LANES + 1, sh.N_SLOTS),
+                                 "%d chunk buffers; %d SMs kept free of hop CTAs" % (sh.N_LANES, sh.N_LANES + 1, sh.N_SLOTS, sh.free_sms),
                         sink="fp64 checksum of the whole output, accumulated in the scan / hop epilogues"),
                     roofline=roofline,
                     breakdown=dict(
