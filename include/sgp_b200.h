@@ -207,6 +207,20 @@ int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int
                     float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
                     int F, int Tc, int* err_flag, double* checksum /*nullable*/, void* stream);
 
+/* Tensor-core hop with fp16x3 operands and 96-row groups (tcgen05 kind::f16; see csrc/spmm_tc16.cu):
+ * same contract as sgp_spmm_rbu_tc.  grp_rows [n_groups, 96]; bimg [total_chunks][96*64] fp16 — per chunk
+ * the [96 rows x 32 columns] slab of operator values times w_scale, split into hi | lo halves stored side
+ * by side in 128-byte rows, K-major SWIZZLE_128B (built by sgp_b200/ops.py::tc16_build).  x_scale: a power
+ * of two with x_scale * max|src| <= 2^14 (the caller must know a bound on the panel: 1 for tanh reservoir
+ * states and their row-stochastic propagations); w_scale: the operator's own power-of-two scale. */
+int sgp_spmm_rbu_tc16(const int32_t* chunk_ptr, const int32_t* grp_rows, const int32_t* cols,
+                      const void* bimg, int n_groups,
+                      const float* src, int64_t src_t_stride, int64_t src_n_stride,
+                      const float* src2, int64_t src2_t_stride, int64_t src2_n_stride, int n_split,
+                      float* dst, int64_t dst_t_stride, int64_t dst_n_stride,
+                      int F, int Tc, float x_scale, float w_scale, int* err_flag,
+                      double* checksum /*nullable*/, void* stream);
+
 /* Process-wide limit on the persistent CTAs of sgp_spmm_rbu_tc (default and maximum: one per SM, 148).
  * The row-sharded encoder lowers it on >= 4 GPUs so that a few SMs stay free for the halo push and
  * the barrier kernels, which cannot share an SM with a hop CTA (registers) and would otherwise wait

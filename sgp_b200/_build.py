@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsgp_b200.so")
 # experiments: SGP_B200_SO=<path> loads another build of the library (tools/build_variants.py)
-SOURCES = ["misc.cu", "csr_build.cu", "reservoir_scan.cu", "khop_spmm.cu", "group_rows.cu", "spmm_tc.cu", "reservoir_tc.cu", "reservoir_tc16.cu", "gesn.cu", "grouped_linear.cu"]
+SOURCES = ["misc.cu", "csr_build.cu", "reservoir_scan.cu", "khop_spmm.cu", "group_rows.cu", "spmm_tc.cu", "spmm_tc16.cu", "reservoir_tc.cu", "reservoir_tc16.cu", "gesn.cu", "grouped_linear.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

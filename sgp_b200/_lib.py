@@ -56,6 +56,9 @@ SIGNATURES = {
     "sgp_spmm_rbu_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64,
                                 c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
+    "sgp_spmm_rbu_tc16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64,
+                                  c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int64, c_int, c_int,
+                                  c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "sgp_tc_set_cta_limit": (c_int, [c_int]),
     "sgp_group_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "sgp_gesn_update": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,

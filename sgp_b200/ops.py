@@ -383,12 +383,113 @@ def spmm_tc(tc: TcOp, src: torch.Tensor, dst: torch.Tensor, halo: Optional[torch
                                  _stream(src.device))
 
 
+@dataclass
+class Tc16Op:
+    """fp16x3 tensor-core operator format, 96-row groups (see sgp_spmm_rbu_tc16 in include/sgp_b200.h)."""
+    chunk_ptr: torch.Tensor      # [n_groups+1] int32
+    grp_rows: torch.Tensor       # [n_groups, 96] int32
+    cols: torch.Tensor           # [total_chunks*32] int32
+    bimg: torch.Tensor           # [total_chunks, 96*64] float16 (hi | lo slab images, pre-swizzled)
+    n_groups: int
+    fill: float
+    w_scale: float               # power of two applied to the operator values
+    inf_norm: float              # max row sum of |values|: bound(S x) <= inf_norm * bound(x)
+    err: torch.Tensor            # device int32 flag
+
+
+TC16_R = 96
+
+
+def _tc16_perm(device) -> torch.Tensor:
+    """Position (in halves) of element (row r, kk) of a chunk's [96 x 64] hi | lo matrix inside its K-major
+    SWIZZLE_128B image: 8-row atoms of 1 KB, 16-byte units XOR (row & 7)."""
+    r = torch.arange(TC16_R, device=device)[:, None]
+    kk = torch.arange(64, device=device)[None, :]
+    return ((r >> 3) * 512 + (r & 7) * 64 + (((kk >> 3) ^ (r & 7)) << 3) + (kk & 7)).reshape(-1)
+
+
+def tc16_build(csr: Csr, grp_rows_h: Optional[np.ndarray] = None, n_cols: Optional[int] = None) -> Tc16Op:
+    """The fp16x3 operator format from a CSR: 96-row locality groups, per group the sorted union of
+    columns padded to chunks of 32, per chunk the [96 x 32] slab of (scaled) values split into fp16
+    hi | lo and laid out as the kernel's shared-memory image."""
+    dev = csr.rowptr.device
+    N, R, KC = csr.num_nodes, TC16_R, TC_KC
+    if grp_rows_h is None:
+        grp_rows_h = group_rows_host(csr.rowptr.cpu().numpy(), csr.col.cpu().numpy(),
+                                     csr.val.cpu().numpy(), N, R)
+    n_groups = grp_rows_h.shape[0]
+    grp_rows = torch.from_numpy(np.ascontiguousarray(grp_rows_h)).to(dev)
+    flat = grp_rows.reshape(-1).to(torch.int64)
+    valid = flat >= 0
+    slot_of = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+    slot_of[flat[valid]] = torch.arange(flat.numel(), device=dev)[valid]
+    counts = (csr.rowptr[1:] - csr.rowptr[:-1]).to(torch.int64)
+    row_of_e = torch.repeat_interleave(torch.arange(N, device=dev), counts)
+    gs = slot_of[row_of_e]
+    g_e, s_e = gs // R, gs % R
+    NC = int(n_cols) if n_cols is not None else N
+    ukey, inv = torch.unique(g_e * NC + csr.col.to(torch.int64), return_inverse=True)
+    ugrp, ucol = ukey // NC, (ukey % NC).to(torch.int32)
+    cnt = torch.bincount(ugrp, minlength=n_groups)
+    chunks = (cnt + KC - 1) // KC
+    chunk_ptr = torch.zeros(n_groups + 1, dtype=torch.int64, device=dev)
+    chunk_ptr[1:] = torch.cumsum(chunks, 0)
+    total_chunks = int(chunk_ptr[-1])
+    first_u = torch.zeros(n_groups + 1, dtype=torch.int64, device=dev)
+    first_u[1:] = torch.cumsum(cnt, 0)
+    pos_u = chunk_ptr[ugrp] * KC + (torch.arange(ukey.numel(), device=dev) - first_u[ugrp])
+    cols = torch.zeros(max(total_chunks * KC, 1), dtype=torch.int32, device=dev)
+    if ukey.numel():
+        fill_col = ucol[first_u[:-1].clamp(max=ukey.numel() - 1)]
+        chunk_grp = torch.repeat_interleave(torch.arange(n_groups, device=dev), chunks)
+        cols[: total_chunks * KC] = fill_col[chunk_grp].repeat_interleave(KC)
+        cols[pos_u] = ucol
+    p_e = pos_u[inv]
+    chunk_e, k_e = p_e // KC, p_e % KC
+    C = max(total_chunks, 1)
+    dense = torch.zeros(C * R * KC, dtype=torch.float32, device=dev)          # [chunk][row][k], duplicates summed
+    dense.index_put_((chunk_e * (R * KC) + s_e * KC + k_e,), csr.val, accumulate=True)
+    wmax = float(dense.abs().max()) if csr.nnz else 0.0
+    w_scale = float(2.0 ** np.floor(np.log2(16384.0 / wmax))) if wmax > 0 else 1.0
+    sc = dense.view(C, R, KC) * w_scale
+    hi = sc.half()
+    lo = (sc - hi.float()).half()
+    del dense, sc
+    bimg = torch.empty(C, R * 64, dtype=torch.float16, device=dev)
+    bimg[:, _tc16_perm(dev)] = torch.cat([hi, lo], dim=2).view(C, R * 64)
+    row_abs = torch.zeros(max(N, 1), device=dev).index_add_(0, row_of_e, csr.val.abs())
+    inf_norm = float(row_abs.max()) if csr.nnz else 0.0
+    fill = csr.nnz / max(int(cnt.sum()) * R, 1)
+    return Tc16Op(chunk_ptr.to(torch.int32), grp_rows.contiguous(), cols, bimg, n_groups, fill, w_scale, inf_norm,
+                  torch.zeros(1, dtype=torch.int32, device=dev))
+
+
+def spmm_tc16(tc: Tc16Op, src: torch.Tensor, dst: torch.Tensor, bound: float, halo: Optional[torch.Tensor] = None,
+              n_split: int = 0, checksum: Optional[torch.Tensor] = None) -> None:
+    """fp16x3 tensor-core hop; `bound` >= max|src| (and |halo|): chooses the power-of-two panel scale."""
+    _require_cuda(src, dst, halo)
+    _check_view3(src, "src")
+    _check_view3(dst, "dst")
+    Tc, _, F = src.shape
+    if not bound > 0:
+        raise ValueError("spmm_tc16 needs a positive bound on |src|")
+    x_scale = float(2.0 ** np.floor(np.log2(16384.0 / (float(bound) * (1 + 1e-6)))))
+    if halo is None:
+        h_ptr, h_ts, h_ns = None, 0, 0
+    else:
+        _check_view3(halo, "halo")
+        h_ptr, h_ts, h_ns = _p(halo), halo.stride(0), halo.stride(1)
+    _call(src.device, "sgp_spmm_rbu_tc16", _p(tc.chunk_ptr), _p(tc.grp_rows), _p(tc.cols), _p(tc.bimg), tc.n_groups,
+          _p(src), src.stride(0), src.stride(1), h_ptr, h_ts, h_ns, n_split, _p(dst), dst.stride(0), dst.stride(1),
+          F, Tc, x_scale, float(tc.w_scale), _p(tc.err), _p(checksum), _stream(src.device))
+
+
 def tc_set_cta_limit(n_ctas: int) -> None:
     """Persistent CTAs per tensor-core hop launch (process-wide; 148 = one per SM)."""
     check(load().sgp_tc_set_cta_limit(int(n_ctas)), "sgp_tc_set_cta_limit")
 
 
-def tc_check(tc: TcOp) -> None:
+def tc_check(tc) -> None:
     """Raise if a tensor-core launch reported an internal barrier timeout (synchronises)."""
     if int(tc.err.item()) != 0:
         raise _lib.SgpError("sgp_spmm_rbu_tc: internal barrier timed out (results invalid)")

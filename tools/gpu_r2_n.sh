@@ -4,7 +4,7 @@ N=${1:-8}
 mkdir -p gpurun_out
 run() { timeout $1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
 port=29540
-for FREE in 0 12 24; do
+for FREE in ${FREES:-0 12 24}; do
   port=$((port+1))
   echo "== bench x$N free_sms=$FREE"; SGP_B200_FREE_SMS=$FREE run 400 $port bench.py --gpus $N --steps 3 --warmup 2 > gpurun_out/n_bench_n${N}_free$FREE.json 2> gpurun_out/n_bench_n${N}_free$FREE.err
   python - <<PY
