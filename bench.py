@@ -306,14 +306,16 @@ def run_own(args, cfg):
             buf = bufs[i % 2][: t1 - t0]
             if timed is None:
                 enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf, acc)
-                enc.sgp_encoder.encode_chunk(buf, F, fwd, bwd, sums, checksum=acc)
+                enc.sgp_encoder.encode_chunk(buf, F, fwd, bwd, sums, checksum=acc, bound=enc.reservoir.state_bound())
             else:
                 timed.wrap("scan", lambda: enc.reservoir.scan_chunk(plan, x_dev[t0:t1], state, buf, acc))
                 for op, base in hop_list:
+                    bnd = enc.reservoir.state_bound()
                     for h in range(1, K + 1):
                         src = buf[..., :F] if h == 1 else buf[..., (base + h - 1) * F:(base + h) * F]
-                        timed.wrap(("spmm", t1 - t0), lambda op=op, src=src, h=h, base=base: op.apply(
-                            src, buf[..., (base + h) * F:(base + h + 1) * F], checksum=acc))
+                        timed.wrap(("spmm", t1 - t0), lambda op=op, src=src, h=h, base=base, bnd=bnd: op.apply(
+                            src, buf[..., (base + h) * F:(base + h + 1) * F], checksum=acc, bound=bnd))
+                        bnd = op.out_bound(bnd)
                 if cfg.get("glob"):
                     g = spatial_blocks(K, bwd is not None)
                     ops.node_sum(buf[..., :F], sums[: t1 - t0])
@@ -356,10 +358,11 @@ def run_own(args, cfg):
     scan_n, scan_ms = summ.get("scan", (0, 0.0))
     scan_flops = N * T * ((2 * H * (Fin + H) + 6 * H) + (L - 1) * (4 * H * H + 6 * H)) * args.steps
     fma_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    hop_kernel = ("spmm_rbu_tc_kernel" if fwd.tc is not None else
+    hop_kernel = ("spmm_rbu_tc16_kernel" if fwd.tc16 is not None else "spmm_rbu_tc_kernel" if fwd.tc is not None else
                   ("spmm_rbu_v3<%d>" % fwd.rbu.R) if fwd.rbu is not None else "spmm_csr_vec")
     traffic = measured_traffic(args.workload, hop_kernel, step_T)
-    roofline = dict(bound="hbm", kernel=hop_kernel + (" (tcgen05, 3xTF32)" if fwd.tc is not None else ""),
+    roofline = dict(bound="hbm", kernel=hop_kernel + (" (tcgen05, fp16x3, 96-row groups)" if fwd.tc16 is not None else
+                                                      " (tcgen05, 3xTF32)" if fwd.tc is not None else ""),
                     achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
                     peak_source=peaks["source"], traffic=traffic,
                     traffic_source=(TRAFFIC_FILE + ": ncu --set full capture of the same kernel and workload, "
@@ -409,7 +412,7 @@ def run_own(args, cfg):
                     "per graph: built once from the host edge list (operator_build_ms, %d B H2D, %d B D2H) "
                     "outside the step, as in the N > 1 lines" %
                     (N * T * D * 4 / 1e9, ei.nbytes + ew.nbytes,
-                     (4 * (N + 1) + 8 * nnz) if (fwd.rbu is not None or fwd.tc is not None) else 0))
+                     (4 * (N + 1) + 8 * nnz) if (fwd.rbu is not None or fwd.tc is not None or fwd.tc16 is not None) else 0))
 
     # ---- CPU baseline on a bounded sample ---------------------------------------------------
     cpu = None
@@ -429,9 +432,9 @@ def run_own(args, cfg):
                 dtype="f32", data="synthetic", config=config_dict(cfg, 1),
                 kernel_config=dict(
                     chunk_steps=step_T,
-                    operator_format=("tcgen05 64-row groups" if fwd.tc is not None else
+                    operator_format=("tcgen05 fp16x3 96-row groups" if fwd.tc16 is not None else "tcgen05 64-row groups" if fwd.tc is not None else
                                      "rbu%d" % fwd.rbu.R if fwd.rbu is not None else "csr"),
-                    group_fill=round((fwd.tc or fwd.rbu).fill, 3) if (fwd.tc or fwd.rbu) else None,
+                    group_fill=round((fwd.tc16 or fwd.tc or fwd.rbu).fill, 3) if (fwd.tc16 or fwd.tc or fwd.rbu) else None,
                     sink="fp64 checksum of the whole output, accumulated in the scan / hop epilogues"),
                 roofline=roofline, reservoir=reservoir, cpu_baseline=cpu, e2e=e2e, clocks=clocks,
                 gpu_launches=int(launches), checksum=checksum_timed)

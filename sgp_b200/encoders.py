@@ -95,11 +95,12 @@ class SGPSpatialEncoder(nn.Module):
                               rbu=self.rbu_mode)
 
     def encode_chunk(self, buf: Tensor, F: int, fwd: ShiftOperator, bwd: Optional[ShiftOperator],
-                     sums: Optional[Tensor] = None, checksum: Optional[Tensor] = None) -> None:
+                     sums: Optional[Tensor] = None, checksum: Optional[Tensor] = None,
+                     bound: Optional[float] = None) -> None:
         """buf [Tc, N, num_blocks*F] (device) with block 0 filled; fills the other blocks.
         `checksum` (device float64 scalar) += the sum of every block written here."""
         k = self.receptive_field
-        propagate_into(buf, F, k, fwd, bwd, checksum)
+        propagate_into(buf, F, k, fwd, bwd, checksum, bound)
         if self.global_attr:
             Tc, N, _ = buf.shape
             if sums is None:
@@ -184,7 +185,7 @@ class SGPEncoder(nn.Module):
             buf = bufs[i % len(bufs)][: t1 - t0]
             xc = x[t0:t1].detach().to(device=dev, dtype=torch.float32, non_blocking=True)
             res.scan_chunk(plan, xc, state, buf, checksum)
-            spat.encode_chunk(buf, F, fwd, bwd, sums, checksum)
+            spat.encode_chunk(buf, F, fwd, bwd, sums, checksum, bound=res.state_bound())
             if sink is not None:
                 sink(t0, t1, buf)
         for op in (fwd, bwd):

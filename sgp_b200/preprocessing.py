@@ -27,16 +27,19 @@ from .reservoir import Reservoir, _cuda_device_for
 _RBU_MIN_NNZ = int(os.environ.get("SGP_B200_RBU_MIN_NNZ", 200_000))
 _RBU_MIN_FILL = {16: 0.30, 8: 0.40, 4: 0.55}
 _TC_MIN_FILL = 0.10      # 64-row groups: the tensor-core hop wins as long as the slabs are >= 10 % dense
+_HOP_DEFAULT = os.environ.get("SGP_B200_HOP", "tc")      # "tc" (3xTF32, 64-row groups) | "tc16" (fp16x3, 96-row groups)
 
 
 class ShiftOperator:
     """Normalised graph-shift operator resident on one GPU (what ``preprocess_adj`` returns)."""
 
     def __init__(self, csr: ops.Csr, rbu: Optional[ops.Rbu] = None, n_split: int = 0,
-                 tc: Optional[ops.TcOp] = None, n_cols: Optional[int] = None):
+                 tc: Optional[ops.TcOp] = None, n_cols: Optional[int] = None,
+                 tc16: Optional[ops.Tc16Op] = None):
         self.csr = csr
         self.rbu = rbu
         self.tc = tc
+        self.tc16 = tc16            # fp16x3 / 96-row format: used when the caller knows a bound on |x|
         self.n_cols = n_cols        # > num rows for a row-sharded (local + halo columns) operator
         self.num_nodes = csr.num_nodes
         self.n_split = n_split      # row-sharded: column ids >= n_split address the halo buffer
@@ -58,15 +61,25 @@ class ShiftOperator:
     def maybe_build_rbu(self, F: int, mode: str = "auto") -> None:
         """Attach a grouped format when it pays (F % 128 == 0 and the greedy groups are dense
         enough): the tensor-core format (64-row groups) first, else the CUDA-core RBU format.
-        mode: "auto" | "off" | "tc" | "rbu" | "force4/8/16"."""
-        if self.rbu is not None or self.tc is not None or mode == "off" or F % 128 != 0:
+        mode: "auto" | "off" | "tc" | "tc16" | "rbu" | "force4/8/16".  "tc16" (or "auto" with
+        SGP_B200_HOP=tc16) builds the fp16x3 / 96-row format INSTEAD of the tf32 one; it serves
+        launches that come with a bound on |x| (the encoders' tanh states), anything else falls to
+        the CSR kernel."""
+        if self.rbu is not None or self.tc is not None or self.tc16 is not None or mode == "off" or F % 128 != 0:
             return
+        if mode == "auto" and _HOP_DEFAULT == "tc16":
+            mode = "auto16"
         if mode == "auto" and self.csr.nnz < _RBU_MIN_NNZ:
             return
         if mode.startswith("force"):
             self.rbu = ops.rbu_build(self.csr, int(mode[len("force"):]), n_cols=self.n_cols)
             return
-        if mode in ("auto", "tc") and (F // 128) in (1, 2, 4):
+        if mode in ("auto16", "tc16") and (F // 128) in (1, 2, 4):
+            cand16 = ops.tc16_build(self.csr, n_cols=self.n_cols)
+            if cand16.fill >= _TC_MIN_FILL * 0.7 or mode == "tc16":
+                self.tc16 = cand16
+                return
+        if mode in ("auto", "auto16", "tc") and (F // 128) in (1, 2, 4):
             cand = ops.tc_build(self.csr, n_cols=self.n_cols)
             if cand.fill >= _TC_MIN_FILL or mode == "tc":
                 self.tc = cand
@@ -78,7 +91,7 @@ class ShiftOperator:
                 return
 
     def apply(self, src: Tensor, dst: Tensor, halo: Optional[Tensor] = None,
-              checksum: Optional[Tensor] = None) -> None:
+              checksum: Optional[Tensor] = None, bound: Optional[float] = None) -> None:
         """dst[t] = S @ src[t] for [T, N, F] device views (dst must not alias src); with `halo`
         [T, n_halo, F] the operator's column ids >= n_split read halo rows.  `checksum` (device
         float64 scalar) += sum(dst): fused into the tensor-core hop's epilogue, a separate
@@ -86,6 +99,9 @@ class ShiftOperator:
         F = src.size(-1)
         aligned = (F % 128 == 0 and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0 and
                    all(s % 4 == 0 for s in (*src.stride()[:2], *dst.stride()[:2])))
+        if self.tc16 is not None and bound is not None and aligned and (F // 128) in (1, 2, 4):
+            ops.spmm_tc16(self.tc16, src, dst, bound, halo, self.n_split, checksum)      # `bound` >= max|src|
+            return
         if self.tc is not None and aligned and (F // 128) in (1, 2, 4):
             ops.spmm_tc(self.tc, src, dst, halo, self.n_split, checksum)
             return
@@ -100,6 +116,16 @@ class ShiftOperator:
         """Raise if a tensor-core launch of this operator reported a barrier timeout (syncs)."""
         if self.tc is not None:
             ops.tc_check(self.tc)
+        if self.tc16 is not None:
+            ops.tc_check(self.tc16)
+
+    def out_bound(self, bound: Optional[float]) -> Optional[float]:
+        """A bound on |S x| given one on |x| (the operator's inf-norm; None stays None)."""
+        if bound is None:
+            return None
+        if self.tc16 is not None:
+            return bound * max(self.tc16.inf_norm, 1e-30) * (1 + 1e-6)
+        return None
 
     def index_select(self, dim: int, index: Tensor) -> "ShiftOperator":
         """``adj.index_select(0, node_index)`` of the reference's mini-batch path
@@ -232,16 +258,23 @@ def spatial_blocks(k: int, bidirectional: bool) -> int:
 
 
 def propagate_into(buf: Tensor, F: int, k: int, fwd: ShiftOperator,
-                   bwd: Optional[ShiftOperator], checksum: Optional[Tensor] = None) -> None:
+                   bwd: Optional[ShiftOperator], checksum: Optional[Tensor] = None,
+                   bound: Optional[float] = None) -> None:
     """buf [T, N, >= blocks*F] on the device with block 0 filled: write S^h x into block h for
     h = 1..k and, with `bwd`, the k hops of the reversed operator into blocks k+1..2k
     (the order of the reference's ``res`` list, sgp_preprocessing.py:200-217)."""
+    # `bound` >= max|block 0| (1 for tanh reservoir states) lets the fp16x3 hop pick its panel scale; every
+    # hop multiplies it by the operator's inf-norm
+    b = bound
     for h in range(1, k + 1):
-        fwd.apply(buf[..., (h - 1) * F:h * F], buf[..., h * F:(h + 1) * F], checksum=checksum)
+        fwd.apply(buf[..., (h - 1) * F:h * F], buf[..., h * F:(h + 1) * F], checksum=checksum, bound=b)
+        b = fwd.out_bound(b)
     if bwd is not None:
+        b = bound
         for h in range(1, k + 1):
             src = buf[..., :F] if h == 1 else buf[..., (k + h - 1) * F:(k + h) * F]
-            bwd.apply(src, buf[..., (k + h) * F:(k + h + 1) * F], checksum=checksum)
+            bwd.apply(src, buf[..., (k + h) * F:(k + h + 1) * F], checksum=checksum, bound=b)
+            b = bwd.out_bound(b)
 
 
 def make_operators(edge_index, edge_weight, num_nodes, *, undirected, add_self_loops,

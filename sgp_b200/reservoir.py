@@ -186,6 +186,11 @@ class Reservoir(nn.Module):
                 plan.append(("cuda", *layer.device_weights(device), float(layer.alpha)))
         return plan
 
+    def state_bound(self) -> Optional[float]:
+        """max |state| of a scan that starts from the zero state: 1 for tanh (and for the self-normalising
+        activation, whose rows have unit norm); unknown for relu."""
+        return 1.0 if self.mode in ("tanh", "self_norm") else None
+
     def multi_layer_ok(self, device=None) -> bool:
         """Small reservoirs (H in {16, 32, 64}) run all their layers in one launch with the weights
         resident in shared memory (sgp_reservoir_scan_multi) when they fit (200 KB)."""

@@ -242,8 +242,10 @@ class RowShardedEncoder:
         self.N_LANES, self.N_SLOTS = int(lanes), int(lanes) + 1
         # SMs left free for the halo push / barrier kernels (they cannot share an SM with a hop CTA)
         import os
+        # measured on C4 (profiles/r2_bench_n8_p2p_free*.json, n4): 12 free SMs give 1447 M against 1314 M
+        # node-steps/s at 8 GPUs and 723 M against 707 M at 4; at 2 GPUs the hop is too long for it to pay
         free = os.environ.get("SGP_B200_FREE_SMS")
-        self.free_sms = int(free) if free is not None else 0
+        self.free_sms = int(free) if free is not None else (12 if self.world >= 4 else 0)
         ops.tc_set_cta_limit(148 - self.free_sms)
         self.exchange_mode, self._peer, self._peer_key = exchange, None, None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -384,6 +386,7 @@ class RowShardedEncoder:
             hs = self.s_hop[lane]
             with torch.cuda.stream(hs):
                 hs.wait_event(scan_done)
+                bounds = [res.state_bound(), res.state_bound()]
                 for oi, (sop, base) in enumerate(((self.fwd, 0), (self.bwd, K))):
                     if sop is None:
                         continue
@@ -394,7 +397,9 @@ class RowShardedEncoder:
                         else:
                             halo = self._exchange(sop, src, lanes[lane]["send"], lanes[lane]["halo"], phase)
                         with phase("hop"):
-                            sop.op.apply(src, buf[..., (base + h) * F:(base + h + 1) * F], halo, checksum)
+                            sop.op.apply(src, buf[..., (base + h) * F:(base + h + 1) * F], halo, checksum,
+                                         bound=bounds[oi])
+                            bounds[oi] = sop.op.out_bound(bounds[oi])
                 if spat.global_attr:
                     with phase("global"):
                         sums = lanes[lane]["sums"][: t1 - t0]

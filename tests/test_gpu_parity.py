@@ -929,3 +929,82 @@ def test_scan_fp16x3_long_recurrence_and_weight_ranges():
         y, _ = run_scan_tc16(x, layers[0])
         ok, worst = O.blockwise_allclose(y, ref, 128)
         assert ok, f"rho={rho} density={density} max|W|={float(layers[0]['w_hh'].abs().max()):.3g}: worst |err|/tol = {worst:.3g}"
+
+
+# ---------------------------------------------------------------- K2-TC16: fp16x3 hop, 96-row groups
+@pytest.mark.parametrize("F", [128, 256, 512])
+@pytest.mark.parametrize("n,k", [(1203, 20), (4000, 100)])
+def test_spmm_fp16x3_vs_oracle(F, n, k):
+    """tcgen05 kind::f16 hop with 96-row groups against the CPU oracle (graph size not a multiple of the
+    group, more time steps than one CTA's time block), inputs bounded by `bound`."""
+    ei, ew = sensor_knn(n, k, seed=F + n)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    tc = ops.tc16_build(op.csr)
+    assert tc.fill > 0.03 and abs(tc.inf_norm - 1.0) < 1e-4
+    rowptr, col, val = O.build_operator(ei, ew, n, set_diag=False)
+    T = 11 if F == 128 else 5
+    x = np.tanh(np.random.default_rng(F).standard_normal((T, n, F))).astype(np.float32)        # |x| < 1
+    buf = torch.zeros(T, n, 2 * F, device=DEV)
+    buf[..., :F] = torch.from_numpy(x).to(DEV)
+    ops.spmm_tc16(tc, buf[..., :F], buf[..., F:], bound=1.0)
+    ops.tc_check(tc)
+    ref = O.spmm(rowptr, col, val, x, impl="c")
+    assert_blocks_close(buf[..., F:].cpu().numpy(), ref, F)
+    chk = torch.empty(T, n, F, device=DEV)
+    ops.spmm(op.csr, buf[..., :F], chk)
+    err = float((buf[..., F:] - chk).abs().max() / chk.abs().max())
+    assert err < 2e-5, err
+    # a larger panel bound only lowers the scale: still fp32-accurate
+    big = torch.from_numpy(50.0 * x).to(DEV).contiguous()
+    out = torch.empty_like(big)
+    ops.spmm_tc16(tc, big, out, bound=50.0)
+    assert float((out - 50.0 * chk).abs().max() / (50.0 * chk.abs().max())) < 2e-5
+
+
+def test_spmm_fp16x3_halo_columns_empty_rows_and_checksum():
+    n, n_own, k, F = 1500, 900, 30, 256
+    ei, ew = sensor_knn(n, k, seed=F)
+    rowptr, col, val = O.build_operator(ei, ew, n, set_diag=False)
+    rp, cl, vl = rowptr[:n_own + 1], col[:rowptr[n_own]], val[:rowptr[n_own]]
+    csr = ops.Csr(torch.from_numpy(rp.astype(np.int32)).to(DEV), torch.from_numpy(cl.astype(np.int32)).to(DEV),
+                  torch.from_numpy(vl.astype(np.float32)).to(DEV), n_own)
+    tc = ops.tc16_build(csr, n_cols=n)
+    T = 5
+    x = np.tanh(np.random.default_rng(F + 1).standard_normal((T, n, F))).astype(np.float32)
+    own = torch.zeros(T, n_own, 2 * F, device=DEV)
+    own[..., :F] = torch.from_numpy(x[:, :n_own]).to(DEV)
+    halo = torch.from_numpy(x[:, n_own:]).to(DEV).permute(1, 0, 2).contiguous().permute(1, 0, 2)
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.spmm_tc16(tc, own[..., :F], own[..., F:], 1.0, halo=halo, n_split=n_own, checksum=acc)
+    ops.tc_check(tc)
+    ref = O.spmm(rowptr, col, val, x, impl="c")[:, :n_own]
+    assert_blocks_close(own[..., F:].cpu().numpy(), ref, F)
+    assert abs(float(acc) - float(own[..., F:].double().sum())) <= 1e-7 * abs(float(acc)) + 1e-6
+    # irregular graph: many empty rows, duplicate edges
+    n2 = 700
+    ei2, ew2 = random_graph(n2, 5000, seed=3)
+    keep = (ei2[1] % 7) != 3
+    op = build_operator(torch.from_numpy(ei2[:, keep]), torch.from_numpy(ew2[keep]), n2, device=DEV)
+    tc2 = ops.tc16_build(op.csr)
+    xx = torch.tanh(torch.randn(3, n2, 256, device=DEV))
+    a, b = torch.full_like(xx, float("nan")), torch.empty_like(xx)
+    ops.spmm_tc16(tc2, xx, a, 1.0)
+    ops.tc_check(tc2)
+    ops.spmm(op.csr, xx, b)
+    assert float((a - b).abs().max()) < 2e-5 * float(b.abs().max())
+
+
+def test_sgp_encoder_with_fp16x3_hop():
+    """SGPEncoder end to end with the fp16x3 hop format (rbu_mode = "tc16": bound 1 from the tanh
+    reservoir, multiplied by the operator's inf-norm per hop), bidirectional + global."""
+    N, k, T, H, K = 3000, 80, 6, 128, 3
+    ei, ew = sensor_knn(N, k, seed=0)
+    x = sensor_signal(T, N, seed=1)
+    torch.manual_seed(2)
+    enc = sgp_b200.SGPEncoder(3, H, 1, 0.9, 0.9, 0.7, 1.0, K, True, False, True)
+    enc.sgp_encoder.rbu_mode = "tc16"
+    y = enc(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ew))
+    fwd, bwd = enc.sgp_encoder.build_operators(torch.from_numpy(ei), torch.from_numpy(ew), N, torch.device(DEV), H)
+    assert fwd.tc16 is not None and bwd.tc16 is not None and fwd.tc is None
+    ref = O.sgp_encoder(x, ei, ew, _layers_of(enc), "tanh", K, True, False, True, impl="c", dtype=torch.float64)
+    assert_blocks_close(y.numpy(), ref, H)
