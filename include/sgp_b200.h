@@ -221,7 +221,7 @@ int sgp_spmm_rbu_tc16(const int32_t* chunk_ptr, const int32_t* grp_rows, const i
                       int F, int Tc, float x_scale, float w_scale, int* err_flag,
                       double* checksum /*nullable*/, void* stream);
 
-/* Process-wide limit on the persistent CTAs of sgp_spmm_rbu_tc (default and maximum: one per SM, 148).
+/* Process-wide limit on the persistent CTAs of sgp_spmm_rbu_tc / sgp_spmm_rbu_tc16 (default and maximum: one per SM, 148).
  * The row-sharded encoder lowers it on >= 4 GPUs so that a few SMs stay free for the halo push and
  * the barrier kernels, which cannot share an SM with a hop CTA (registers) and would otherwise wait
  * for the gap between two hop launches. */

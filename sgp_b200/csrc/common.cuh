@@ -14,6 +14,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int> g_tc_cta_limit;   // persistent CTAs per tensor-core hop launch (sgp_tc_set_cta_limit)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -4,6 +4,7 @@
 namespace sgp {
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_tc_cta_limit{kNumSMs};
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -168,6 +169,12 @@ static int grid_1d(int64_t total, int threads) {
 }  // namespace sgp
 
 using namespace sgp;
+
+extern "C" int sgp_tc_set_cta_limit(int n_ctas) {
+    SGP_REQUIRE(n_ctas >= 1, SGP_EINVAL, "sgp_tc_set_cta_limit: n_ctas=%d", n_ctas);
+    g_tc_cta_limit.store(n_ctas < kNumSMs ? n_ctas : kNumSMs, std::memory_order_relaxed);
+    return SGP_OK;
+}
 
 extern "C" int sgp_version(void) { return SGP_B200_ABI_VERSION; }
 extern "C" const char* sgp_last_error(void) { return g_err; }

@@ -582,15 +582,7 @@ const TcKnobs& tc_knobs() {
     static const TcKnobs k;
     return k;
 }
-// persistent CTAs per launch (<= one per SM); see sgp_tc_set_cta_limit
-std::atomic<int> g_tc_cta_limit{sgp::kNumSMs};
 }  // namespace
-
-extern "C" int sgp_tc_set_cta_limit(int n_ctas) {
-    SGP_REQUIRE(n_ctas >= 1, SGP_EINVAL, "sgp_tc_set_cta_limit: n_ctas=%d", n_ctas);
-    g_tc_cta_limit.store(n_ctas < sgp::kNumSMs ? n_ctas : sgp::kNumSMs, std::memory_order_relaxed);
-    return SGP_OK;
-}
 
 extern "C" int sgp_spmm_rbu_tc(const int32_t* chunk_ptr, const int32_t* grp_rows, const int32_t* cols,
                                const float* bimg, int n_groups, const float* src, int64_t src_t_stride,

@@ -439,7 +439,8 @@ extern "C" int sgp_spmm_rbu_tc16(const int32_t* chunk_ptr, const int32_t* grp_ro
     const long long n_work_ll = (long long)n_groups * ny;
     SGP_REQUIRE(n_work_ll < (1ll << 31), SGP_EUNSUPPORTED, "sgp_spmm_rbu_tc16: too many work items");
     const int n_work = (int)n_work_ll;
-    const int grid = n_work < kNumSMs ? n_work : kNumSMs;
+    const int cta_limit = g_tc_cta_limit.load(std::memory_order_relaxed);
+    const int grid = n_work < cta_limit ? n_work : cta_limit;      // persistent: one CTA per SM (fewer on sharded runs)
     const float inv_scale = 1.f / (x_scale * w_scale);
 #define SGP_T16(NFC_, HALO_)                                                                           \
     do {                                                                                               \

@@ -22,7 +22,7 @@ import torch
 from torch import nn, Tensor
 
 from . import ops
-from .preprocessing import (ShiftOperator, _chunk_steps, make_operators, propagate_into,
+from .preprocessing import (ShiftOperator, _chunk_steps, make_operators, panel_bound, propagate_into,
                             spatial_blocks)
 from .reservoir import Reservoir, _cuda_device_for
 
@@ -125,7 +125,7 @@ class SGPSpatialEncoder(nn.Module):
             t1 = min(T, t0 + step)
             buf = out[t0:t1] if x.is_cuda else torch.empty(t1 - t0, N, D, device=dev)
             buf[..., :F] = x3[t0:t1].to(device=dev, dtype=torch.float32)
-            self.encode_chunk(buf, F, fwd, bwd)
+            self.encode_chunk(buf, F, fwd, bwd, bound=panel_bound(buf[..., :F]) if fwd.tc16 is not None else None)
             if not x.is_cuda:
                 out[t0:t1] = buf.to(x.device)
         for op in (fwd, bwd):

@@ -27,7 +27,10 @@ from .reservoir import Reservoir, _cuda_device_for
 _RBU_MIN_NNZ = int(os.environ.get("SGP_B200_RBU_MIN_NNZ", 200_000))
 _RBU_MIN_FILL = {16: 0.30, 8: 0.40, 4: 0.55}
 _TC_MIN_FILL = 0.10      # 64-row groups: the tensor-core hop wins as long as the slabs are >= 10 % dense
-_HOP_DEFAULT = os.environ.get("SGP_B200_HOP", "tc")      # "tc" (3xTF32, 64-row groups) | "tc16" (fp16x3, 96-row groups)
+# tensor-core hop format chosen by "auto": "tc16" (fp16x3, 96-row groups: 75.5 us per hop-panel at C4) or
+# "tc" (3xTF32, 64-row groups: 92.1 us); tc16 needs a bound on |x| per launch — the encoders know it (tanh
+# states), the generic entry points take max|x| of their input
+_HOP_DEFAULT = os.environ.get("SGP_B200_HOP", "tc16")
 
 
 class ShiftOperator:
@@ -153,7 +156,7 @@ class ShiftOperator:
         lead = xd.shape[:-2]
         x3 = xd.reshape(-1, xd.size(-2), xd.size(-1)).contiguous()
         out = torch.empty(x3.size(0), self.num_nodes, x3.size(-1), device=dev)
-        self.apply(x3, out)
+        self.apply(x3, out, bound=panel_bound(x3) if self.tc16 is not None else None)
         return out.reshape(*lead, *out.shape[-2:]).to(x.device)
 
 
@@ -188,6 +191,12 @@ def _sparse_to_edges(adj):
     convention ``edge_index = [col (source j); row (target i)]`` (``col, row = edge_index``, :80)."""
     row, col, value = adj.coo()
     return torch.stack([torch.as_tensor(col), torch.as_tensor(row)]).to(torch.int64), value, int(adj.sparse_sizes()[0])
+
+
+def panel_bound(x: Tensor) -> float:
+    """max |x| of a device panel (one reduction + a sync): the bound the fp16x3 hop needs when the
+    caller has no analytic one."""
+    return max(float(x.abs().max()), 1e-30) if x.numel() else 1.0
 
 
 Adj = Union[Tensor, np.ndarray, ShiftOperator, SparseAdj]
@@ -445,7 +454,7 @@ def sgp_spatial_embedding(x, num_nodes, edge_index, edge_weight=None, k=2, undir
         buf[..., :F0] = x3[t0:t1].to(device=dev, dtype=torch.float32)
         if one_hot_encoding:
             buf[..., F0:F] = torch.eye(num_nodes, device=dev)
-        propagate_into(buf, F, k, fwd, bwd)
+        propagate_into(buf, F, k, fwd, bwd, bound=panel_bound(buf[..., :F]) if fwd.tc16 is not None else None)
         if not x.is_cuda:
             out[t0:t1] = buf.to(x.device)
     for op in (fwd, bwd):

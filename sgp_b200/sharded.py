@@ -426,8 +426,9 @@ class RowShardedEncoder:
         (results invalid).  Synchronises the device and the group."""
         bad = 0
         for sop in self.operators:
-            if sop.op.tc is not None:
-                bad |= int(sop.op.tc.err.item() != 0)
+            for fmt in (sop.op.tc, sop.op.tc16):
+                if fmt is not None:
+                    bad |= int(fmt.err.item() != 0)
         for entry in getattr(self, "_plan_for_check", []) or []:
             if entry[0] in ("tc", "tc16"):
                 bad |= int(entry[-1].item() != 0)
@@ -471,6 +472,7 @@ def encode_sharded_lockstep(encoder, edge_index, edge_weight, num_nodes: int, x:
         res.check_plan(plan)
         bufs.append(buf)
     for o, base in zip(range(len(shards)), (0, K)):
+        bound = res.state_bound()
         for h in range(1, K + 1):
             sl = slice(0, F) if h == 1 else slice((base + h - 1) * F, (base + h) * F)
             # pack on every shard, then "exchange": rank p's halo segment from q = q's send segment for p
@@ -488,8 +490,9 @@ def encode_sharded_lockstep(encoder, edge_index, edge_weight, num_nodes: int, x:
                 halo = torch.cat(parts, 0) if parts else torch.empty(0, T, F, device=dev)
                 assert halo.shape[0] == sop.plan.n_halo
                 sop.op.apply(bufs[r][..., sl], bufs[r][..., (base + h) * F:(base + h + 1) * F],
-                             halo.permute(1, 0, 2))
+                             halo.permute(1, 0, 2), bound=bound)
                 sop.op.check()
+            bound = max((s_.op.out_bound(bound) or 0.0) for s_ in shards[o]) or None
     out = torch.empty(T, num_nodes, D, device=dev)
     if spat.global_attr:
         g = spatial_blocks(K, spat.bidirectional)
@@ -623,7 +626,8 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
         fmt = sh.fwd.op
         hop_ms = float(bd_max[names.index("hop")])
         achieved = float(local_bytes) / (hop_ms * 1e-3) / 1e9 if hop_ms else 0.0
-        roofline = dict(bound="hbm", kernel="spmm_rbu_tc_kernel<HALO> on %d shards" % world if fmt.tc is not None else "spmm (CUDA cores)",
+        roofline = dict(bound="hbm", kernel=("spmm_rbu_tc16_kernel<HALO> on %d shards" % world if fmt.tc16 is not None else
+                                             "spmm_rbu_tc_kernel<HALO> on %d shards" % world if fmt.tc is not None else "spmm (CUDA cores)"),
                         achieved=achieved, peak=peaks["hbm_gbs"] * world, unit="GB/s",
                         frac=achieved / (peaks["hbm_gbs"] * world), peak_source=peaks["source"] + " x n_gpus",
                         traffic=None, algorithmic_bytes_per_pass_all_ranks=float(local_bytes),
@@ -637,7 +641,7 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
                     config=config_dict(cfg, world),
                     kernel_config=dict(
                         chunk_steps=step, halo_rows_per_owned_row=float(halo[0] / halo[1]),
-                        operator_format=("tcgen05 64-row groups" if fmt.tc is not None else
+                        operator_format=("tcgen05 fp16x3 96-row groups" if fmt.tc16 is not None else "tcgen05 64-row groups" if fmt.tc is not None else
                                          "rbu%d" % fmt.rbu.R if fmt.rbu is not None else "csr"),
                         partition="recursive bisection along the patch diameter (sgp_partition_rows)",
                         exchange=sh.exchange_used + " of halo rows per hop; scan + %d hop chains on %d streams, "

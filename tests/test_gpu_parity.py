@@ -511,8 +511,9 @@ def test_sgp_encoder_baseline_shapes_vs_oracle(c):
     # which kernels the dispatch picks for this shape (deterministic: same calls as forward makes)
     fwd, bwd = enc.sgp_encoder.build_operators(torch.from_numpy(ei), torch.from_numpy(ew), N, torch.device(DEV), H)
     plan = enc.reservoir.device_plan(torch.device(DEV), N)
-    assert (fwd.tc is not None) == c["tc"] and (plan[0][0] in ("tc", "tc16")) == c["tc"]
-    assert (bwd is not None) == bidir and (bwd is None or (bwd.tc is not None) == c["tc"])
+    on_tc = lambda op: op.tc is not None or op.tc16 is not None      # noqa: E731  (tcgen05 hop: fp16x3 by default)
+    assert on_tc(fwd) == c["tc"] and (plan[0][0] in ("tc", "tc16")) == c["tc"]
+    assert (bwd is not None) == bidir and (bwd is None or on_tc(bwd) == c["tc"])
     del fwd, bwd, plan
     ref = O.sgp_encoder(x, ei, ew, _layers_of(enc), "tanh", K, bidir, und, glob, add_self_loops=loops,
                         impl="c", dtype=torch.float64)
@@ -595,7 +596,8 @@ def test_spmm_rbu_wide_features_and_gather_paths():
 
 # ---------------------------------------------------------------- row-sharded path on one GPU
 @pytest.mark.parametrize("world,kw", [(2, dict()), (3, dict(bidir=True, glob=True)),
-                                      (4, dict(undirected=True, loops=True, glob=True))])
+                                      (4, dict(undirected=True, loops=True, glob=True)),
+                                      (2, dict(mode="tc16")), (3, dict(bidir=True, mode="tc16"))])
 def test_row_sharded_lockstep_equals_single_gpu(world, kw):
     """The sharded encoder's plans and device kernels (halo pack, second-source tensor-core SpMM,
     per-operator halo plans of the bidirectional / undirected encoders) on ONE GPU: `world` shards
@@ -608,7 +610,7 @@ def test_row_sharded_lockstep_equals_single_gpu(world, kw):
     enc = sgp_b200.SGPEncoder(3, H, 1, 0.9, 0.9, 0.7, 1.0, K, kw.get("bidir", False), False,
                               kw.get("glob", False), add_self_loops=kw.get("loops", False),
                               undirected=kw.get("undirected", False))
-    enc.sgp_encoder.rbu_mode = "tc"
+    enc.sgp_encoder.rbu_mode = kw.get("mode", "tc")
     full = enc(x.to(DEV), torch.from_numpy(ei).to(DEV), torch.from_numpy(ew).to(DEV))
     got = encode_sharded_lockstep(enc, torch.from_numpy(ei), torch.from_numpy(ew), N, x, world, DEV)
     err = float((got - full).abs().max() / full.abs().max())
