@@ -285,11 +285,15 @@ def run_own(args, cfg):
     x_dev = torch.from_numpy(x).to(dev)
     ei_h, ew_h = torch.from_numpy(ei), torch.from_numpy(ew)
     # the operator is per graph: built once from the HOST edge list, timed on its own
-    torch.cuda.synchronize()
-    t_b0 = time.perf_counter()
-    fwd, bwd = enc.sgp_encoder.build_operators(ei_h, ew_h, N, dev, F)
-    torch.cuda.synchronize()
-    build_ms = (time.perf_counter() - t_b0) * 1e3
+    build_times = []
+    for _ in range(2):          # the first build also pays CUDA's lazy module loading and the allocator's first growth
+        fwd = bwd = None
+        torch.cuda.synchronize()
+        t_b0 = time.perf_counter()
+        fwd, bwd = enc.sgp_encoder.build_operators(ei_h, ew_h, N, dev, F)
+        torch.cuda.synchronize()
+        build_times.append((time.perf_counter() - t_b0) * 1e3)
+    build_ms = build_times[-1]
     plan = enc.reservoir.device_plan(dev, N)
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     bufs = [torch.empty(step_T, N, D, device=dev) for _ in range(2)]
@@ -406,6 +410,7 @@ def run_own(args, cfg):
     e2e_s = sum(t_e2e) / len(t_e2e)
     e2e = dict(value=N * T / e2e_s, unit=UNIT, h2d_bytes_per_step=int(x.nbytes), d2h_bytes_per_step=8,
                ms_per_step=e2e_s * 1e3, checksum=chk_e2e, operator_build_ms=build_ms,
+               operator_build_first_call_ms=build_times[0],
                note="SGPEncoder.encode_stream on the pinned host series: H2D of x chunk by chunk, scan + K "
                     "hops, checksum fused into the kernels' epilogues, D2H of the checksum; the [T,N,D] output "
                     "itself (%.0f GB) is not copied back.  The operator (CSR + row grouping + slab images) is "
