@@ -12,6 +12,7 @@ torch_geometric runs in the sm_100a kernels behind ``include/sgp_b200.h``:
 """
 from __future__ import annotations
 
+import math
 import os
 from typing import List, Optional, Union
 
@@ -102,7 +103,8 @@ class ShiftOperator:
         F = src.size(-1)
         aligned = (F % 128 == 0 and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0 and
                    all(s % 4 == 0 for s in (*src.stride()[:2], *dst.stride()[:2])))
-        if self.tc16 is not None and bound is not None and aligned and (F // 128) in (1, 2, 4):
+        if (self.tc16 is not None and bound is not None and math.isfinite(bound) and bound > 0 and aligned and
+                (F // 128) in (1, 2, 4)):
             ops.spmm_tc16(self.tc16, src, dst, bound, halo, self.n_split, checksum)      # `bound` >= max|src|
             return
         if self.tc is not None and aligned and (F // 128) in (1, 2, 4):
@@ -196,7 +198,7 @@ def _sparse_to_edges(adj):
 def panel_bound(x: Tensor) -> float:
     """max |x| of a device panel (one reduction + a sync): the bound the fp16x3 hop needs when the
     caller has no analytic one."""
-    return max(float(x.abs().max()), 1e-30) if x.numel() else 1.0
+    return float(x.abs().max()) if x.numel() else 0.0      # nan / inf / 0 make apply() take the plain CSR kernel
 
 
 Adj = Union[Tensor, np.ndarray, ShiftOperator, SparseAdj]

@@ -1010,3 +1010,27 @@ def test_sgp_encoder_with_fp16x3_hop():
     assert fwd.tc16 is not None and bwd.tc16 is not None and fwd.tc is None
     ref = O.sgp_encoder(x, ei, ew, _layers_of(enc), "tanh", K, True, False, True, impl="c", dtype=torch.float64)
     assert_blocks_close(y.numpy(), ref, H)
+
+
+def test_generic_entry_points_bound_and_non_finite_inputs():
+    """op @ x and sgp_spatial_embedding on arbitrary (unbounded, partly non-finite) panels: the fp16x3 hop
+    takes max|x| as its bound; NaN / inf panels take the CSR kernel and keep IEEE semantics."""
+    n, k, F = 2600, 90, 128
+    ei, ew = sensor_knn(n, k, seed=4)
+    op = build_operator(torch.from_numpy(ei), torch.from_numpy(ew), n, device=DEV)
+    op.maybe_build_rbu(F, "tc16")
+    assert op.tc16 is not None
+    rowptr, col, val = O.build_operator(ei, ew, n, set_diag=False)
+    x = (1e3 * np.random.default_rng(0).standard_normal((2, n, F))).astype(np.float32)
+    y = op @ torch.from_numpy(x)
+    assert_blocks_close(y.numpy(), O.spmm(rowptr, col, val, x, impl="c"), F)
+    xb = x.copy()
+    xb[0, 17, 5] = np.nan
+    xb[1, 40, 7] = np.inf
+    yb = (op @ torch.from_numpy(xb)).numpy()
+    ref = O.spmm(rowptr, col, val, xb, impl="c")
+    assert np.array_equal(np.isnan(yb), np.isnan(ref)) and np.array_equal(np.isinf(yb), np.isinf(ref))
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(yb[fin], ref[fin], rtol=1e-4, atol=1e-2)
+    z = op @ torch.zeros(1, n, F)
+    assert float(z.abs().max()) == 0.0
