@@ -240,6 +240,8 @@ class RowShardedEncoder:
         lanes: hop chains in flight (streams); lanes + 1 chunk buffers."""
         self.enc, self.group, self.dev = encoder, group, torch.device(device)
         self.N_LANES, self.N_SLOTS = int(lanes), int(lanes) + 1
+        self.exchange_mode, self._peer, self._peer_key = exchange, None, None
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         # SMs left free for the halo push / barrier kernels (they cannot share an SM with a hop CTA)
         import os
         # measured on C4 (profiles/r2_bench_n8_p2p_free*.json, n4): 12 free SMs give 1447 M against 1314 M
@@ -247,8 +249,6 @@ class RowShardedEncoder:
         free = os.environ.get("SGP_B200_FREE_SMS")
         self.free_sms = int(free) if free is not None else (12 if self.world >= 4 else 0)
         ops.tc_set_cta_limit(148 - self.free_sms)
-        self.exchange_mode, self._peer, self._peer_key = exchange, None, None
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         spat = encoder.sgp_encoder
         if spat.undirected:
             assert spat.bidirectional is False

@@ -136,3 +136,46 @@ def test_halo_exchange_over_gloo(world):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=10) == 1.0
+
+
+def test_row_sharded_encoder_constructor_on_cpu(monkeypatch, tmp_path):
+    """RowShardedEncoder.__init__ end to end on the CPU (world_size 1 over gloo), with the device pieces
+    stubbed: partition, per-operator plans of a bidirectional encoder, free-SM default, stream set-up."""
+    import sgp_b200
+    from sgp_b200 import sharded
+
+    class _FullOp:
+        def __init__(self, arrs):
+            self.arrs = arrs
+
+        def csr_arrays(self):
+            return tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in self.arrs)
+
+    def fake_build_operator(edge_index, edge_weight, num_nodes, *, gcn_norm=False, set_diag=False, remove_diag=False,
+                            symmetrize=False, transpose=False, normalize=True, device=None):
+        ei = np.asarray(edge_index)
+        if transpose:
+            ei = ei[[1, 0]]
+        return _FullOp(O.build_operator(ei, np.asarray(edge_weight), num_nodes, gcn_norm=gcn_norm, set_diag=set_diag))
+
+    class _StubShardedOperator:
+        def __init__(self, plan, device, F, rbu_mode="auto"):
+            self.plan, self.op = plan, None
+
+    limits = []
+    monkeypatch.setattr(sharded, "build_operator", fake_build_operator)
+    monkeypatch.setattr(sharded, "ShardedOperator", _StubShardedOperator)
+    monkeypatch.setattr(sharded.ops, "tc_set_cta_limit", limits.append)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: object())
+    dist.init_process_group("gloo", init_method=f"file://{tmp_path}/rdzv", rank=0, world_size=1)
+    try:
+        n = 300
+        ei, ew = sensor_knn(n, 8, seed=1)
+        torch.manual_seed(0)
+        enc = sgp_b200.SGPEncoder(3, 16, 1, 0.9, 0.9, 0.7, 1.0, 2, True, False, True)
+        sh = sharded.RowShardedEncoder(enc, torch.from_numpy(ei), torch.from_numpy(ew), n, "cpu")
+        assert sh.world == 1 and sh.free_sms == 0 and limits == [148]
+        assert sh.bwd is not None and np.array_equal(sh.bwd.plan.own, sh.fwd.plan.own) and sh.plan.n_own == n
+        assert sh.halo_rows() == 0 and len(sh.operators) == 2 and len(sh.s_hop) == 2
+    finally:
+        dist.destroy_process_group()
