@@ -40,7 +40,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the warm-up to the end of the timed
+    region (a multi-GPU pass is tens of milliseconds: with the timed region alone there may be no sample);
+    the median is over the samples under load."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -51,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -326,12 +328,12 @@ def run_own(args, cfg):
                     ops.node_mean_broadcast(sums[: t1 - t0], N, buf[..., g * F:(g + 1) * F])
                     ops.checksum_view(buf[..., g * F:(g + 1) * F], acc)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         one_pass()
     torch.cuda.synchronize()
     acc.zero_()
-    sampler = ClockSampler(local)
-    sampler.start()
     timed = Timed()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

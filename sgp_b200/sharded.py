@@ -548,14 +548,14 @@ def bench(args, cfg, rank, world, dev, peaks, config_dict, metric, unit, clock_s
     def one_pass(breakdown=None):
         sh.encode_stream(x_own, None, chunk_steps=step, checksum=acc, breakdown=breakdown)
 
+    sampler = clock_sampler(dev.index) if (clock_sampler is not None and rank == 0) else None
+    if sampler is not None:
+        sampler.start()                  # from the warm-up on: a timed pass is tens of ms, the sampler ticks every 50 ms
     for _ in range(args.warmup):
         one_pass()
     torch.cuda.synchronize()
     sh.check()
     acc.zero_()
-    sampler = clock_sampler(dev.index) if (clock_sampler is not None and rank == 0) else None
-    if sampler is not None:
-        sampler.start()
     dist.barrier()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
