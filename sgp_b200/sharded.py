@@ -257,7 +257,7 @@ class RowShardedEncoder:
         # the full operators, exactly as SGPSpatialEncoder builds them (make_operators), then cut
         full = build_operator(edge_index, edge_weight, num_nodes, gcn_norm=spat.undirected,
                               set_diag=spat.add_self_loops, symmetrize=spat.undirected, device=self.dev)
-        rowptr, col, val = (a.cpu().numpy() for a in full.csr_arrays())
+        rowptr, col, val = ops.to_host(*full.csr_arrays())
         del full
         self.owner = partition_rows(rowptr, col, num_nodes, self.world)
         self.plan = build_plans(rowptr, col, val, num_nodes, self.world, ranks=[self.rank],
@@ -267,7 +267,7 @@ class RowShardedEncoder:
         if spat.bidirectional:
             rev = build_operator(edge_index, edge_weight, num_nodes, gcn_norm=False,
                                  set_diag=spat.add_self_loops, transpose=True, device=self.dev)
-            rowptr, col, val = (a.cpu().numpy() for a in rev.csr_arrays())
+            rowptr, col, val = ops.to_host(*rev.csr_arrays())
             del rev
             plan_b = build_plans(rowptr, col, val, num_nodes, self.world, ranks=[self.rank],
                                  owner=self.owner)[0]
@@ -456,7 +456,7 @@ def encode_sharded_lockstep(encoder, edge_index, edge_weight, num_nodes: int, x:
     owner, shards = None, []           # shards[o][r] = ShardedOperator
     for spec in specs:
         full = build_operator(edge_index, edge_weight, num_nodes, device=dev, **spec)
-        rowptr, col, val = (a.cpu().numpy() for a in full.csr_arrays())
+        rowptr, col, val = ops.to_host(*full.csr_arrays())
         if owner is None:
             owner = partition_rows(rowptr, col, num_nodes, world)
         plans = build_plans(rowptr, col, val, num_nodes, world, owner=owner)
