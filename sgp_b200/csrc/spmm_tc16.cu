@@ -235,7 +235,6 @@ spmm_rbu_tc16_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __res
             const int a = grp;
             const int it = it0 + a, s = it & (kT16Stages - 1);
             if (!t16_warp_wait(&full[s], (it >> 3) & 1, &abort_s, err, lane)) return false;
-            if (cc > 0 && !t16_warp_wait(&afree[a], (cc - 1) & 1, &abort_s, err, lane)) return false;
             const uint32_t rs = smem_base + s * kT16StageBytes + m * 4;     // row-major stage: [k][feature]
             const uint32_t ta = lane_addr + kT16AOff + a * 32;
             uint32_t hv[16], lv[16];
@@ -250,15 +249,20 @@ spmm_rbu_tc16_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __res
                 hv[k >> 1] = t16_bits(h2);
                 lv[k >> 1] = t16_bits(__floats2half2_rn(s0 - hf.x, s1 - hf.y));
             }
+            // the stage is in registers now: hand it back to the producers, and only then wait for the MMAs
+            // that still read this accumulator's A tile — the conversion of chunk c + 1 runs under the MMAs of chunk c
+            __syncwarp();
+            if (lane == 0) t16_mbar_arrive(&empty[s]);
+            if (cc > 0) {
+                if (!t16_warp_wait(&afree[a], (cc - 1) & 1, &abort_s, err, lane)) return false;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             SGP_T16_ST16(ta, hv);
             SGP_T16_ST16(ta + 16, lv);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) {
-                t16_mbar_arrive(&ready[a]);
-                t16_mbar_arrive(&empty[s]);
-            }
+            if (lane == 0) t16_mbar_arrive(&ready[a]);
             ++cc;
             it0 += kT16Acc;
             return true;
