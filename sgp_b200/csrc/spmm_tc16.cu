@@ -30,10 +30,16 @@ constexpr int kT16Acc = 4;           // accumulators per CTA (time steps x featu
 constexpr int kT16SplitWarps = 16;   // 4 groups x TMEM lane quarter
 constexpr int kT16ProducerWarps = 4;
 constexpr int kT16Issuers = 2;
-constexpr int kT16Stages = 8;        // gathered-row ring
+#ifndef SGP_T16_STAGES
+#define SGP_T16_STAGES 8
+#endif
+#ifndef SGP_T16_BBUFS
+#define SGP_T16_BBUFS 3
+#endif
+constexpr int kT16Stages = SGP_T16_STAGES;   // gathered-row ring
 constexpr int kT16StageBytes = kT16KC * 128 * 4;     // 16 KB: 32 rows x 128 features fp32, row-major
 constexpr int kT16BBytes = kT16R * 128;              // 12 KB: [96 rows][32 hi | 32 lo] fp16
-constexpr int kT16BBufs = 3;
+constexpr int kT16BBufs = SGP_T16_BBUFS;
 constexpr size_t kT16Smem = (size_t)kT16Stages * kT16StageBytes + kT16BBufs * kT16BBytes + 1024;
 constexpr int kT16TmemCols = 512;    // [0, 384) four accumulators of 96 columns, [384, 512) four A tiles of 16 hi + 16 lo columns
 constexpr int kT16AOff = kT16Acc * kT16R;
@@ -117,7 +123,9 @@ spmm_rbu_tc16_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __res
                      const float* __restrict__ src2, int64_t s2_ts, uint32_t s2_nb, int n_split,
                      float* __restrict__ dst, int64_t d_ts, int64_t d_ns, int Tc,
                      float x_scale, float inv_scale, int* err, double* __restrict__ chk) {
-    static_assert(kT16Acc == 4 && kT16Stages == 8, "index arithmetic below");
+    // every accumulator's chain must own its stages (stage = item % stages, accumulator = item % 4): a ring whose depth
+    // is not a multiple of 4 lets one chain wait for a stage another chain holds — a deadlock (11 stages: barrier time-out)
+    static_assert(kT16Acc == 4 && kT16Stages % kT16Acc == 0 && kT16Smem <= 227 * 1024, "ring depth / shared memory");
     constexpr int TB = kT16Acc / NFC;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (t16_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -199,8 +207,8 @@ spmm_rbu_tc16_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __res
                     const long long nxt = (c + 1 < n_chunks) ? (long long)(c_beg + c + 1) : first_chunk_of(ws + 1);
                     if (nxt >= 0) coln = __ldg(cols + (size_t)nxt * kT16KC + lane);
                 }
-                const int s = it & (kT16Stages - 1);
-                if (it >= kT16Stages && !t16_warp_wait(&empty[s], ((it >> 3) + 1) & 1, &abort_s, err, lane)) { ok = false; break; }
+                const int s = it % kT16Stages;
+                if (it >= kT16Stages && !t16_warp_wait(&empty[s], ((it / kT16Stages) + 1) & 1, &abort_s, err, lane)) { ok = false; break; }
                 if (pw == 0 && bph > 0 && !t16_warp_wait(&bfree[bi], (bph - 1) & 1, &abort_s, err, lane)) { ok = false; break; }
                 const uint32_t dstp = dst0 + s * kT16StageBytes, fbar = full0 + s * 8;
 #pragma unroll
@@ -233,8 +241,8 @@ spmm_rbu_tc16_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __res
         double csum = 0.0;
         auto convert_item = [&]() -> bool {
             const int a = grp;
-            const int it = it0 + a, s = it & (kT16Stages - 1);
-            if (!t16_warp_wait(&full[s], (it >> 3) & 1, &abort_s, err, lane)) return false;
+            const int it = it0 + a, s = it % kT16Stages;
+            if (!t16_warp_wait(&full[s], (it / kT16Stages) & 1, &abort_s, err, lane)) return false;
             const uint32_t rs = smem_base + s * kT16StageBytes + m * 4;     // row-major stage: [k][feature]
             const uint32_t ta = lane_addr + kT16AOff + a * 32;
             uint32_t hv[16], lv[16];
