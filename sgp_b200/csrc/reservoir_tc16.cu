@@ -75,11 +75,12 @@ __device__ __forceinline__ bool r16_wait(uint64_t* bar, uint32_t parity, volatil
     }
     return false;
 }
-__device__ __forceinline__ float r16_tanh(float x) {      // as in reservoir_tc.cu: 1e-7 absolute
+constexpr float kR16TanhC = 2.885390081777927f;           // 2 log2 e
+__device__ __forceinline__ float r16_rcp_ex2p1(float y) {  // 1 / (2^y + 1); tanh(z) = 1 - 2 r at y = 2 z log2 e (1e-7 absolute)
     float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-    return fmaf(-2.f, r, 1.f);
+    return r;
 }
 
 #define SGP_R16_LD32(addr, v)                                                                        \
@@ -163,9 +164,9 @@ reservoir_tc16_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, i
     }
     for (int i = tid; i < FINP * H; i += kR16Threads) {
         const int f = i / H, n = i % H;
-        wih_s[i] = (f < Fin) ? w_ih[(size_t)n * Fin + f] : 0.f;
-    }
-    for (int i = tid; i < H; i += kR16Threads) bias_s[i] = bias[i];
+        wih_s[i] = (f < Fin) ? w_ih[(size_t)n * Fin + f] * kR16TanhC : 0.f;      // pre-activation in units of
+    }                                                                              // 1 / (2 log2 e): see the blend
+    for (int i = tid; i < H; i += kR16Threads) bias_s[i] = bias[i] * kR16TanhC;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(r16_smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
@@ -247,6 +248,9 @@ reservoir_tc16_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, i
         bool store_pending = false;
         double csum = 0.0;
         const float oma_s = oma * (1.f / kR16StateScale);      // exact: a power of two
+        // tanh(z) = 1 - 2 / (2^(2 z log2 e) + 1): the factor 2 log2 e is folded into inv_scale, the bias and W_ih
+        // (z arrives as the ex2 argument), and alpha * tanh = alpha - 2 alpha r is one FMA
+        const float inv_c = inv_scale * kR16TanhC, m2a = -2.f * alpha;
         for (int t = 0; t < Tc && ok; ++t) {
             float xn[FINP];
 #pragma unroll
@@ -273,8 +277,8 @@ reservoir_tc16_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, i
 #pragma unroll
                     for (int e = 0; e < 8; e += 4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j + e);
-                        float z[4] = {fmaf(__uint_as_float(d[j + e]), inv_scale, b4.x), fmaf(__uint_as_float(d[j + e + 1]), inv_scale, b4.y),
-                                      fmaf(__uint_as_float(d[j + e + 2]), inv_scale, b4.z), fmaf(__uint_as_float(d[j + e + 3]), inv_scale, b4.w)};
+                        float z[4] = {fmaf(__uint_as_float(d[j + e]), inv_c, b4.x), fmaf(__uint_as_float(d[j + e + 1]), inv_c, b4.y),
+                                      fmaf(__uint_as_float(d[j + e + 2]), inv_c, b4.z), fmaf(__uint_as_float(d[j + e + 3]), inv_c, b4.w)};
 #pragma unroll
                         for (int f = 0; f < FINP; ++f) {
                             const float4 w4 = *reinterpret_cast<const float4*>(wih_s + f * H + c0 + j + e);
@@ -286,8 +290,8 @@ reservoir_tc16_kernel(const float* __restrict__ x, int64_t x_ts, int64_t x_ns, i
                             // old state = (hi + lo) / 2^14, folded into the blend: oma_s = (1 - alpha) / 2^14
                             const float2 hf = __half22float2(r16_half2(hp[(e + p2) >> 1]));
                             const float2 lf = __half22float2(r16_half2(lo_old[(j + e + p2) >> 1]));
-                            hn[j + e + p2] = fmaf(oma_s, hf.x, fmaf(oma_s, lf.x, alpha * r16_tanh(z[p2])));
-                            hn[j + e + p2 + 1] = fmaf(oma_s, hf.y, fmaf(oma_s, lf.y, alpha * r16_tanh(z[p2 + 1])));
+                            hn[j + e + p2] = fmaf(oma_s, hf.x, fmaf(oma_s, lf.x, fmaf(m2a, r16_rcp_ex2p1(z[p2]), alpha)));
+                            hn[j + e + p2 + 1] = fmaf(oma_s, hf.y, fmaf(oma_s, lf.y, fmaf(m2a, r16_rcp_ex2p1(z[p2 + 1]), alpha)));
                         }
                     }
                 }
