@@ -29,7 +29,10 @@ constexpr int kT16KC = 32;           // union columns per chunk
 constexpr int kT16Acc = 4;           // accumulators per CTA (time steps x feature chunks)
 constexpr int kT16SplitWarps = 16;   // 4 groups x TMEM lane quarter
 constexpr int kT16ProducerWarps = 4;
-constexpr int kT16Issuers = 2;
+#ifndef SGP_T16_ISSUERS
+#define SGP_T16_ISSUERS 1          // measured on one box: 1 / 2 / 4 issuers = 73.0 / 74.1 / 75.3 us per hop-panel (profiles/r2_issuers.txt)
+#endif
+constexpr int kT16Issuers = SGP_T16_ISSUERS;   // MMA issuer warps (one elected thread each); accumulator a belongs to issuer a % issuers
 #ifndef SGP_T16_STAGES
 #define SGP_T16_STAGES 8
 #endif
@@ -111,8 +114,8 @@ __device__ __forceinline__ bool t16_warp_wait(uint64_t* bar, uint32_t parity, vo
 
 __device__ __forceinline__ uint32_t t16_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
-// Warp roles (22 warps): 0-15 split (group = accumulator index, warp & 3 = TMEM lane quarter), 16-19
-// producers (cp.async gathers; producer 0 also fetches the slab images), 20-21 MMA issuers.
+// Warp roles (21 warps): 0-15 split (group = accumulator index, warp & 3 = TMEM lane quarter), 16-19
+// producers (cp.async gathers; producer 0 also fetches the slab images), 20 the MMA issuer.
 // mbarriers as in spmm_tc.cu, minus the raw-slab hand-off (bfull is completed by the TMA bytes).
 template <int NFC, bool HALO>
 __global__ void __launch_bounds__(kT16Threads, 1)
@@ -343,7 +346,7 @@ spmm_rbu_tc16_kernel(const int32_t* __restrict__ chunk_ptr, const int32_t* __res
             if (lane == 0) atomicAdd(chk, csum);
         }
     } else {
-        // ================= MMA issuers: two warps, ONE elected thread each ========================
+        // ================= MMA issuer(s): kT16Issuers warps, ONE elected thread each ================
         // kind::f16, fp32 accumulate, A from TMEM (lane = feature, fp16 pairs along k), B K-major smem,
         // N = 96, M = 128, K = 16: 6 MMAs of 48 cycles per item
         if (t16_elect_one()) {
