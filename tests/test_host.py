@@ -258,3 +258,12 @@ def test_small_reservoirs_choose_the_fused_multi_layer_plan():
     assert sgp_b200.Reservoir(3, 16, num_layers=8).multi_layer_ok()            # sgp_pv.yaml
     assert not sgp_b200.Reservoir(3, 128, num_layers=1).multi_layer_ok()       # tensor-core / tiled kernels
     assert not sgp_b200.Reservoir(3, 64, num_layers=8).multi_layer_ok()        # weights exceed shared memory
+
+
+def test_to_host_passes_cpu_tensors_through():
+    """ops.to_host stages CUDA tensors through pinned memory; CPU tensors come back as numpy views."""
+    from sgp_b200 import ops
+    a, b = torch.arange(5, dtype=torch.int32), torch.linspace(0, 1, 4)
+    ha, hb = ops.to_host(a, b)
+    assert isinstance(ha, np.ndarray) and ha.dtype == np.int32 and ha.tolist() == [0, 1, 2, 3, 4]
+    assert hb.dtype == np.float32 and np.shares_memory(hb, b.numpy())
