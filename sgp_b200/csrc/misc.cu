@@ -124,7 +124,9 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int64_t s_ts, 
 // that fits beside the persistent hop CTAs (which leave 6.6 K registers per SM) did overlap with the
 // SpMM of the other chunk — and slowed that SpMM by 24 % (its single-thread issue loops share the
 // schedulers), 292 ms per pass at 2 GPUs against 272 ms for this shape, which runs in the gap
-// between two hop launches at NVLink rate.
+// between two hop launches at NVLink rate.  (Measured against the tf32 hop.  The fp16x3 hop's CTA leaves
+// 9-12 K registers, so ONE CTA of this shape can sit beside it; the 2 / 4 / 8-GPU lines of the final
+// kernels were measured in that configuration, with 12 SMs kept free of hop CTAs from 4 GPUs up.)
 __global__ void push_rows_kernel(const float* __restrict__ src, int64_t s_ts, int64_t s_ns,
                                  const int32_t* __restrict__ index, const int64_t* __restrict__ dst_addr,
                                  int n_index, int64_t d_ts, int F4, int Tc) {
